@@ -1,0 +1,107 @@
+/* univid_b200 -- C ABI of the B200-native Wan DiT attention hot path.
+ *
+ * The reference (AIGeeksGroup/UniVid) is pure Python: its "FFI" for this path is the set of
+ * third-party kernel calls made from models/wan/utils/modules/{attention,model}.py and
+ * models/wan/distributed/{ulysses,util,sequence_parallel}.py.  Each entry point below replaces
+ * one of those call sites (cited per function).  Conventions:
+ *   - every pointer named q/k/v/o/..._in/_out is a DEVICE pointer; `grid_fhw` and the stride
+ *     arrays are HOST pointers read during the call;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - functions return 0 on success, a negative uvb_status otherwise; the message is available
+ *     from uvb_last_error() (thread-local); nothing throws, allocates device memory or
+ *     synchronises the device;
+ *   - there is no CPU fallback: without an sm_100 device the compute calls fail with
+ *     UVB_ERR_CUDA / UVB_ERR_UNSUPPORTED.
+ */
+#ifndef UNIVID_B200_H_
+#define UNIVID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum uvb_status {
+  UVB_OK = 0,
+  UVB_ERR_INVALID = -1,     /* bad argument (null pointer, shape, alignment) */
+  UVB_ERR_UNSUPPORTED = -2, /* head_dim != 128, device is not sm_100, ... */
+  UVB_ERR_CUDA = -3         /* CUDA runtime / driver error; see uvb_last_error() */
+};
+
+enum uvb_dtype { UVB_BF16 = 0, UVB_F32 = 1 };
+
+/* Library ABI version (major*100 + minor). */
+int uvb_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* uvb_last_error(void);
+
+/* Fused WanRMSNorm(q), WanRMSNorm(k) over the full width dim = N*128, followed by the 3-D RoPE.
+ * Replaces: WanRMSNorm.forward (model.py:77-85) x2 + rope_apply (model.py:38-66) x2 of
+ * WanSelfAttention.forward (model.py:137-147); with cos_sin == NULL it is the norm-only prologue of
+ * WanCrossAttention.forward (model.py:170-171); tok_offset > 0 is the rank slice of the
+ * sequence-parallel rope_apply (distributed/sequence_parallel.py:23-61).
+ *
+ *   q_in, k_in   [B, L, N*128] in `in_dtype` (either may be NULL to skip that tensor)
+ *   wq, wk       [N*128] fp32 RMSNorm weights
+ *   cos_sin      [1024, 64, 2] fp32 (cos, sin) of the reference `freqs` table (model.py:398-405),
+ *                or NULL for no rotation
+ *   row_scale    [L] fp32 or NULL; pre_bias [N*128] fp32 or NULL: when pre_bias != NULL the k row is
+ *                first mapped to row_scale[l]*k + pre_bias (text-weighted context, model_pipeline.py:1789-1797
+ *                folded through the k projection)
+ *   q_out, k_out bf16; element (b, l, n, d) is written at
+ *                b*out_sb + l*out_sl + (n / hpg)*out_sg + (n % hpg)*128 + d     (element strides)
+ *                hpg = N, out_sg = 0 gives plain [B, L, N, 128]; hpg = N/p gives the Ulysses send
+ *                layout [p][B][L][N/p][128] (util.py:27 chunk(scatter_dim=2) fused into the store)
+ *   grid_fhw     HOST int32 [B, 3] token grid (f, h, w) per sample (B <= 8), NULL iff cos_sin NULL
+ *   tok_offset   global index of local token 0; tokens >= f*h*w are normalised but not rotated
+ */
+int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const float* wq,
+                     const float* wk, const float* cos_sin, const float* row_scale,
+                     const float* pre_bias, void* q_out, void* k_out, int B, int L, int N,
+                     const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
+                     int64_t out_sl, int64_t out_sg, void* stream);
+
+/* Pure copy of v [B, L, N, 128] bf16 into the same grouped layout as above.
+ * Replaces: the chunk(...).contiguous() pack of all_to_all (distributed/util.py:27). */
+int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, int hpg,
+                          int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream);
+
+/* softmax(q k^T * scale) v, non-causal, head_dim 128, bf16, fp32 accumulation.
+ * Replaces: flash_attn_varlen_func / flash_attn_interface / F.scaled_dot_product_attention at
+ * attention.py:96,113,175 as reached from flash_attention() (attention.py:24) and attention()
+ * (attention.py:133).
+ *
+ *   q [B, Lq, N, 128], k/v [B, Lk, N, 128], o [B, Lq, N, 128]; *_strides are HOST int64[3]
+ *   = (batch, token, head) strides in elements, NULL = contiguous.  All strides must be multiples
+ *   of 8 elements and every base pointer 16-byte aligned.
+ *   k_lens  DEVICE int32 [B] or NULL: keys >= k_lens[b] are masked (attention.py:72-80).
+ *   scale   softmax scale (reference default: 128^-0.5).
+ */
+int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
+                      int B, int Lq, int Lk, int N, const int64_t* q_strides,
+                      const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
+                      float scale, void* stream);
+
+/* Cross-attention with per-key modifiers fused (UniVid "Temperature Modality Alignment").
+ * Replaces: WanCrossAttention.forward's flash_attention call (model.py:175) as entered through
+ * Wan22ContextWrapper.hooked_forward (model_pipeline.py:1756-1803).
+ *   key_logit_scale  DEVICE fp32 [ceil128(Lk)] or NULL: logits[:, j] *= key_logit_scale[j]
+ *                    (a per-key temperature on the text keys)
+ *   key_pv_weight    DEVICE fp32 [ceil128(Lk)] or NULL: probabilities are multiplied by w[j] AFTER
+ *                    normalisation (out = sum_j p_j w_j v_j / sum_j p_j); with v = bias-free value
+ *                    projection this equals scaling context rows by w_j (SURVEY.md A7')
+ *   out_bias         DEVICE fp32 [N*128] or NULL, added to the normalised output (the value bias)
+ */
+int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
+                       const float* key_logit_scale, const float* key_pv_weight,
+                       const float* out_bias, int B, int Lq, int Lk, int N,
+                       const int64_t* q_strides, const int64_t* k_strides,
+                       const int64_t* v_strides, const int64_t* o_strides, float scale,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIVID_B200_H_ */

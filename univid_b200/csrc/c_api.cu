@@ -1,0 +1,255 @@
+// C ABI of libunivid_b200.so (see include/univid_b200.h).  Host side only: argument checks,
+// TMA tensor-map construction and kernel launches.  No torch types, no device allocation, no sync.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/univid_b200.h"
+#include "fmha_fwd_sm100.cuh"
+#include "qk_norm_rope.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define UVB_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(UVB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));   \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime, so the library loads (and exports its
+// symbols) on hosts without a driver.
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+int check_device() {
+  static int ok_dev = -1;
+  int dev = 0;
+  UVB_CUDA(cudaGetDevice(&dev));
+  if (dev == ok_dev) return UVB_OK;
+  int major = 0;
+  UVB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10)
+    return fail(UVB_ERR_UNSUPPORTED, "device %d has compute capability %d.x; sm_100 required", dev,
+                major);
+  ok_dev = dev;
+  return UVB_OK;
+}
+
+// [B, L, N, 128] bf16 viewed as (d, token, head, batch); box = one 64-column panel of a 128-token tile
+int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const int64_t* strides) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  int64_t sb = static_cast<int64_t>(L) * N * 128, sl = static_cast<int64_t>(N) * 128, sh = 128;
+  if (strides != nullptr) {
+    sb = strides[0];
+    sl = strides[1];
+    sh = strides[2];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return fail(UVB_ERR_INVALID, "tensor base pointer must be 16-byte aligned");
+  if (sl % 8 != 0 || sh % 8 != 0 || sb % 8 != 0 || sl <= 0 || sh <= 0 || sb <= 0)
+    return fail(UVB_ERR_INVALID, "strides must be positive multiples of 8 elements");
+  const cuuint64_t gdim[4] = {128, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(N),
+                              static_cast<cuuint64_t>(B)};
+  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(sl) * 2, static_cast<cuuint64_t>(sh) * 2,
+                              static_cast<cuuint64_t>(sb) * 2};
+  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return UVB_OK;
+}
+
+constexpr int kFmhaStages = 4;
+
+template <bool kKeyMod>
+int launch_fmha(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
+                const float* key_logit_scale, const float* key_pv_weight, const float* out_bias,
+                int B, int Lq, int Lk, int N, const int64_t* qs, const int64_t* ks,
+                const int64_t* vs, const int64_t* os, float scale, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
+    return fail(UVB_ERR_INVALID, "null tensor pointer");
+  if (B <= 0 || Lq <= 0 || Lk <= 0 || N <= 0 || B > 65535 || N > 65535)
+    return fail(UVB_ERR_INVALID, "bad shape B=%d Lq=%d Lk=%d N=%d", B, Lq, Lk, N);
+  if (!(scale > 0.f)) return fail(UVB_ERR_INVALID, "softmax scale must be positive");
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+
+  uvb::FmhaParams p;
+  memset(&p, 0, sizeof(p));
+  if ((rc = make_tile_map(&p.tm_q, q, B, Lq, N, qs)) != UVB_OK) return rc;
+  if ((rc = make_tile_map(&p.tm_k, k, B, Lk, N, ks)) != UVB_OK) return rc;
+  if ((rc = make_tile_map(&p.tm_v, v, B, Lk, N, vs)) != UVB_OK) return rc;
+  if ((rc = make_tile_map(&p.tm_o, o, B, Lq, N, os)) != UVB_OK) return rc;
+  p.k_lens = k_lens;
+  p.key_logit_scale = key_logit_scale;
+  p.key_pv_weight = key_pv_weight;
+  p.out_bias = out_bias;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+
+  auto kern = uvb::fmha_fwd_kernel<kFmhaStages, kKeyMod>;
+  constexpr int smem = uvb::FmhaSmem<kFmhaStages>::kDynBytes;
+  UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const dim3 grid((Lq + uvb::kQTiles * uvb::kBlockM - 1) / (uvb::kQTiles * uvb::kBlockM), N, B);
+  kern<<<grid, uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
+}
+
+template <typename InT>
+int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(p.B) * p.L;
+  const unsigned blocks = static_cast<unsigned>((rows + uvb::kNormRopeWarps - 1) / uvb::kNormRopeWarps);
+  const dim3 block(uvb::kNormRopeWarps * 32);
+  const int dim = p.N * 128;
+  switch (dim) {
+    case 1536: uvb::qk_norm_rope_kernel<InT, 6><<<blocks, block, 0, stream>>>(p); break;
+    case 2048: uvb::qk_norm_rope_kernel<InT, 8><<<blocks, block, 0, stream>>>(p); break;
+    case 3072: uvb::qk_norm_rope_kernel<InT, 12><<<blocks, block, 0, stream>>>(p); break;
+    case 5120: uvb::qk_norm_rope_kernel<InT, 20><<<blocks, block, 0, stream>>>(p); break;
+    default: uvb::qk_norm_rope_kernel<InT, 0><<<blocks, block, 0, stream>>>(p); break;
+  }
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvb_version(void) { return 100; }
+
+const char* uvb_last_error(void) { return g_err; }
+
+int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const float* wq,
+                     const float* wk, const float* cos_sin, const float* row_scale,
+                     const float* pre_bias, void* q_out, void* k_out, int B, int L, int N,
+                     const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
+                     int64_t out_sl, int64_t out_sg, void* stream) {
+  if (q_in == nullptr && k_in == nullptr) return fail(UVB_ERR_INVALID, "q_in and k_in are both null");
+  if ((q_in != nullptr && (wq == nullptr || q_out == nullptr)) ||
+      (k_in != nullptr && (wk == nullptr || k_out == nullptr)))
+    return fail(UVB_ERR_INVALID, "missing weight or output pointer");
+  if (B <= 0 || L <= 0 || N <= 0) return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d", B, L, N);
+  if (in_dtype != UVB_BF16 && in_dtype != UVB_F32) return fail(UVB_ERR_INVALID, "bad in_dtype %d", in_dtype);
+  if (hpg <= 0 || N % hpg != 0) return fail(UVB_ERR_INVALID, "hpg=%d must divide N=%d", hpg, N);
+  if (cos_sin != nullptr && grid_fhw == nullptr)
+    return fail(UVB_ERR_INVALID, "grid_fhw is required when cos_sin is given");
+  if (cos_sin != nullptr && B > uvb::kMaxBatchGrid)
+    return fail(UVB_ERR_UNSUPPORTED, "B=%d > %d samples per call with RoPE", B, uvb::kMaxBatchGrid);
+  if (out_sb % 8 != 0 || out_sl % 8 != 0 || out_sg % 8 != 0)
+    return fail(UVB_ERR_INVALID, "output strides must be multiples of 8 elements");
+  if ((row_scale != nullptr) != (pre_bias != nullptr) && row_scale != nullptr)
+    return fail(UVB_ERR_INVALID, "row_scale requires pre_bias");
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+
+  uvb::NormRopeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q_in = q_in;
+  p.k_in = k_in;
+  p.wq = wq;
+  p.wk = wk;
+  p.cos_sin = reinterpret_cast<const float2*>(cos_sin);
+  p.row_scale = row_scale;
+  p.pre_bias = pre_bias;
+  p.q_out = static_cast<__nv_bfloat16*>(q_out);
+  p.k_out = static_cast<__nv_bfloat16*>(k_out);
+  p.B = B;
+  p.L = L;
+  p.N = N;
+  if (cos_sin != nullptr) {
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < 3; ++i) {
+        const int g = grid_fhw[3 * b + i];
+        if (g <= 0 || g > 1024) return fail(UVB_ERR_INVALID, "grid size %d out of (0, 1024]", g);
+        p.grid[b][i] = g;
+      }
+    }
+  }
+  p.tok_offset = tok_offset;
+  p.eps = eps;
+  p.hpg = hpg;
+  p.out_sb = out_sb;
+  p.out_sl = out_sl;
+  p.out_sg = out_sg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return in_dtype == UVB_BF16 ? launch_norm_rope<__nv_bfloat16>(p, st) : launch_norm_rope<float>(p, st);
+}
+
+int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, int hpg,
+                          int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream) {
+  if (v_in == nullptr || v_out == nullptr) return fail(UVB_ERR_INVALID, "null pointer");
+  if (B <= 0 || L <= 0 || N <= 0 || hpg <= 0 || N % hpg != 0)
+    return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d hpg=%d", B, L, N, hpg);
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+  uvb::HeadScatterParams p;
+  p.in = static_cast<const __nv_bfloat16*>(v_in);
+  p.out = static_cast<__nv_bfloat16*>(v_out);
+  p.B = B;
+  p.L = L;
+  p.N = N;
+  p.hpg = hpg;
+  p.out_sb = out_sb;
+  p.out_sl = out_sl;
+  p.out_sg = out_sg;
+  const long long total = static_cast<long long>(B) * L * N * 16;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  uvb::head_scatter_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
+}
+
+int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
+                      int B, int Lq, int Lk, int N, const int64_t* q_strides,
+                      const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
+                      float scale, void* stream) {
+  return launch_fmha<false>(q, k, v, o, k_lens, nullptr, nullptr, nullptr, B, Lq, Lk, N, q_strides,
+                            k_strides, v_strides, o_strides, scale, stream);
+}
+
+int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
+                       const float* key_logit_scale, const float* key_pv_weight,
+                       const float* out_bias, int B, int Lq, int Lk, int N,
+                       const int64_t* q_strides, const int64_t* k_strides,
+                       const int64_t* v_strides, const int64_t* o_strides, float scale,
+                       void* stream) {
+  return launch_fmha<true>(q, k, v, o, k_lens, key_logit_scale, key_pv_weight, out_bias, B, Lq, Lk,
+                           N, q_strides, k_strides, v_strides, o_strides, scale, stream);
+}
+
+}  // extern "C"

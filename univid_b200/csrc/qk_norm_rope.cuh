@@ -1,0 +1,286 @@
+// Fused q/k WanRMSNorm (over the full model width) + 3-D RoPE prologue, HBM-bound.
+// Reference math: WanRMSNorm.forward  models/wan/utils/modules/model.py:77-85
+//                 rope_apply          models/wan/utils/modules/model.py:38-66
+//                 SP rope_apply       models/wan/distributed/sequence_parallel.py:23-61 (tok_offset)
+// Rounding points mirror the reference under bf16 autocast: the normalised value is rounded to the
+// input dtype (`.type_as(x)`), multiplied by the fp32 weight, rotated, and rounded once to bf16
+// (the cast the reference performs at flash_attention() entry, attention.py:59-83).
+//
+// One warp owns one token row.  Lane l holds the 16-byte vectors v = l + 32*i of the row, so every
+// vector of a lane has the same offset inside its head (d0 = 8*(l%16)): the lane needs just four
+// (cos, sin) pairs per token, shared by all heads and by q and k.  All loads of a row are issued
+// before the first use (VPL independent 128-bit loads per lane), the sum of squares is reduced with
+// warp shuffles, and the row is written back with 128-bit stores.
+#pragma once
+#include "ptx.cuh"
+
+namespace uvb {
+
+constexpr int kMaxBatchGrid = 8;
+
+struct NormRopeParams {
+  const void* q_in;        // [B, L, dim]  (InT)
+  const void* k_in;        // [B, L, dim]  or nullptr
+  const float* wq;         // [dim]
+  const float* wk;         // [dim]
+  const float2* cos_sin;   // [1024][64] (cos, sin) of the concatenated (f | h | w) bands, or nullptr
+  const float* row_scale;  // [L] or nullptr: x <- row_scale[l] * x + pre_bias (applied to k only)
+  const float* pre_bias;   // [dim] or nullptr
+  __nv_bfloat16* q_out;
+  __nv_bfloat16* k_out;
+  int B, L, N;             // dim = N * 128
+  int grid[kMaxBatchGrid][3];   // (f, h, w) per sample
+  int tok_offset;          // global index of local token 0 (sequence-parallel shard)
+  float eps;
+  // output addressing: elem(b, l, n, d) = b*out_sb + l*out_sl + (n / hpg)*out_sg + (n % hpg)*128 + d
+  int hpg;                 // heads per group (N for plain [B,L,N,128])
+  long long out_sb, out_sl, out_sg;
+};
+
+template <typename InT>
+struct RowVec;  // 8 consecutive elements
+
+template <>
+struct RowVec<__nv_bfloat16> {
+  uint4 raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                 : "l"(p));
+  }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  // `.type_as(x)`: round the normalised value to the input dtype
+  static __device__ __forceinline__ float round_in(float x) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+  }
+};
+
+template <>
+struct RowVec<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ float round_in(float x) { return x; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Normalise + rotate one row held in registers and store it.
+template <typename InT, int VPL>
+__device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const float* __restrict__ w,
+                                              __nv_bfloat16* __restrict__ out_row, int hpg,
+                                              long long out_sg, int dim, float eps, bool rotate,
+                                              const float (&cs)[8], float rscale,
+                                              const float* __restrict__ pre_bias, int lane) {
+  RowVec<InT> v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i].load(in + (lane + 32 * i) * 8);
+
+  float ss = 0.f;
+  float x[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].unpack(x[i]);
+    if (pre_bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + 32 * i) * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + 32 * i) * 8) + 1);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[i][e] = RowVec<InT>::round_in(fmaf(rscale, x[i][e], bb[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(x[i][e], x[i][e], ss);
+  }
+  ss = warp_sum(ss);
+  const float rinv = rsqrtf(ss / static_cast<float>(dim) + eps);
+
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + 32 * i;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vec * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vec * 8) + 1);
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = RowVec<InT>::round_in(x[i][e] * rinv) * ww[e];
+    uint32_t o[4];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      float a = y[2 * pr], b = y[2 * pr + 1];
+      if (rotate) {
+        const float c = cs[2 * pr], s = cs[2 * pr + 1];
+        const float ra = a * c - b * s;
+        const float rb = fmaf(a, s, b * c);
+        a = ra;
+        b = rb;
+      }
+      o[pr] = pack_bf16x2(a, b);
+    }
+    const int n = vec >> 4;            // head index
+    const int d0 = (vec & 15) * 8;     // offset inside the head
+    __nv_bfloat16* dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o[0]),
+                 "r"(o[1]), "r"(o[2]), "r"(o[3])
+                 : "memory");
+  }
+}
+
+// Generic-width variant (dim = 256 * nvec_per_lane not known at compile time): two passes over the
+// row, the second one served by L1/L2.
+template <typename InT>
+__device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in,
+                                                      const float* __restrict__ w,
+                                                      __nv_bfloat16* __restrict__ out_row, int hpg,
+                                                      long long out_sg, int dim, float eps,
+                                                      bool rotate, const float (&cs)[8],
+                                                      float rscale,
+                                                      const float* __restrict__ pre_bias, int lane) {
+  const int nvec = dim / 8;
+  float ss = 0.f;
+  for (int vec = lane; vec < nvec; vec += 32) {
+    RowVec<InT> v;
+    v.load(in + vec * 8);
+    float x[8];
+    v.unpack(x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (pre_bias != nullptr) x[e] = RowVec<InT>::round_in(fmaf(rscale, x[e], pre_bias[vec * 8 + e]));
+      ss = fmaf(x[e], x[e], ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rinv = rsqrtf(ss / static_cast<float>(dim) + eps);
+  for (int vec = lane; vec < nvec; vec += 32) {
+    RowVec<InT> v;
+    v.load(in + vec * 8);
+    float x[8];
+    v.unpack(x);
+    uint32_t o[4];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      float a = x[2 * pr], b = x[2 * pr + 1];
+      if (pre_bias != nullptr) {
+        a = RowVec<InT>::round_in(fmaf(rscale, a, pre_bias[vec * 8 + 2 * pr]));
+        b = RowVec<InT>::round_in(fmaf(rscale, b, pre_bias[vec * 8 + 2 * pr + 1]));
+      }
+      a = RowVec<InT>::round_in(a * rinv) * w[vec * 8 + 2 * pr];
+      b = RowVec<InT>::round_in(b * rinv) * w[vec * 8 + 2 * pr + 1];
+      if (rotate) {
+        const float c = cs[2 * pr], s = cs[2 * pr + 1];
+        const float ra = a * c - b * s;
+        const float rb = fmaf(a, s, b * c);
+        a = ra;
+        b = rb;
+      }
+      o[pr] = pack_bf16x2(a, b);
+    }
+    const int n = vec >> 4;
+    const int d0 = (vec & 15) * 8;
+    __nv_bfloat16* dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+constexpr int kNormRopeWarps = 8;
+
+// VPL = dim / 256 (vectors per lane); VPL == 0 selects the generic two-pass path.
+template <typename InT, int VPL>
+__global__ void __launch_bounds__(kNormRopeWarps * 32)
+qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long row = static_cast<long long>(blockIdx.x) * kNormRopeWarps + warp;
+  if (row >= static_cast<long long>(p.B) * p.L) return;
+  const int b = static_cast<int>(row / p.L);
+  const int l = static_cast<int>(row % p.L);
+  const int dim = p.N * 128;
+
+  // (cos, sin) for pairs jj = 4*(lane%16) .. +3 of this token
+  float cs[8];
+  bool rotate = false;
+  if (p.cos_sin != nullptr) {
+    const int gb = b < kMaxBatchGrid ? b : kMaxBatchGrid - 1;
+    const int gh = p.grid[gb][1], gw = p.grid[gb][2];
+    const int tok = p.tok_offset + l;
+    rotate = tok < p.grid[gb][0] * gh * gw;   // padding tokens pass through unrotated (model.py:62)
+    if (rotate) {
+      const int pf = tok / (gh * gw), ph = (tok / gw) % gh, pw = tok % gw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int jj = 4 * (lane & 15) + i;
+        const int pos = jj < 22 ? pf : (jj < 43 ? ph : pw);   // bands: 22 | 21 | 21 (model.py:43)
+        const float2 v = __ldg(p.cos_sin + pos * 64 + jj);
+        cs[2 * i] = v.x;
+        cs[2 * i + 1] = v.y;
+      }
+    }
+  }
+  if (!rotate) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+  }
+
+  const long long in_off = row * dim;
+  const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
+  const InT* q_in = static_cast<const InT*>(p.q_in);
+  const InT* k_in = static_cast<const InT*>(p.k_in);
+  const float rscale = p.row_scale != nullptr ? p.row_scale[l] : 1.0f;
+  if constexpr (VPL > 0) {
+    if (q_in != nullptr)
+      norm_rope_row<InT, VPL>(q_in + in_off, p.wq, p.q_out + out_off, p.hpg, p.out_sg, dim, p.eps,
+                              rotate, cs, 1.0f, nullptr, lane);
+    if (k_in != nullptr)
+      norm_rope_row<InT, VPL>(k_in + in_off, p.wk, p.k_out + out_off, p.hpg, p.out_sg, dim, p.eps,
+                              rotate, cs, rscale, p.pre_bias, lane);
+  } else {
+    if (q_in != nullptr)
+      norm_rope_row_generic<InT>(q_in + in_off, p.wq, p.q_out + out_off, p.hpg, p.out_sg, dim,
+                                 p.eps, rotate, cs, 1.0f, nullptr, lane);
+    if (k_in != nullptr)
+      norm_rope_row_generic<InT>(k_in + in_off, p.wk, p.k_out + out_off, p.hpg, p.out_sg, dim,
+                                 p.eps, rotate, cs, rscale, p.pre_bias, lane);
+  }
+}
+
+// Head-group scatter of an un-normalised tensor (v) into the Ulysses send layout; pure copy.
+struct HeadScatterParams {
+  const __nv_bfloat16* in;   // [B, L, N, 128]
+  __nv_bfloat16* out;
+  int B, L, N, hpg;
+  long long out_sb, out_sl, out_sg;
+};
+
+__global__ void __launch_bounds__(256) head_scatter_kernel(const __grid_constant__ HeadScatterParams p) {
+  const long long nvec_row = static_cast<long long>(p.N) * 16;   // 16-byte vectors per token
+  const long long total = static_cast<long long>(p.B) * p.L * nvec_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / nvec_row;
+    const int vec = static_cast<int>(i % nvec_row);
+    const int b = static_cast<int>(row / p.L), l = static_cast<int>(row % p.L);
+    const int n = vec >> 4, d0 = (vec & 15) * 8;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(p.in) + i);
+    __nv_bfloat16* dst = p.out + b * p.out_sb + l * p.out_sl +
+                         static_cast<long long>(n / p.hpg) * p.out_sg + (n % p.hpg) * 128 + d0;
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+}
+
+}  // namespace uvb

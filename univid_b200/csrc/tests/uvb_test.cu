@@ -1,0 +1,410 @@
+// Stand-alone GPU check + timing of libunivid_b200.so through its C ABI (no torch).
+// Usage: uvb_test <case> [args]   -- one case per process so a trapped kernel cannot poison the next.
+//   fmha  B Lq Lk N klen keymod iters     compare with a naive fp32 kernel (if Lq*Lk small) and time
+//   prol  B L N rope dtype iters          compare with a double-precision host reference and time
+// Test infrastructure only; nothing here is part of the product library.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../../include/univid_b200.h"
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e = (x);                                                                   \
+    if (e != cudaSuccess) {                                                                \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e)); \
+      exit(2);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+static uint32_t g_seed = 12345;
+static float frand() {  // uniform(-1, 1)
+  g_seed = g_seed * 1664525u + 1013904223u;
+  return ((g_seed >> 8) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+static float nrand() {  // ~N(0,1) (sum of uniforms)
+  float s = 0;
+  for (int i = 0; i < 6; ++i) s += frand();
+  return s * 0.70710678f;
+}
+
+// one warp per query row, online softmax in fp32
+__global__ void naive_attn(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                           float* o, const int* k_lens, const float* kls, const float* pvw,
+                           const float* bias, int B, int Lq, int Lk, int N, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= (long long)B * Lq * N) return;
+  const int n = row % N;
+  const int lq = (row / N) % Lq;
+  const int b = row / ((long long)N * Lq);
+  const int klen = k_lens ? min(k_lens[b], Lk) : Lk;
+  const __nv_bfloat16* qp = q + (((long long)b * Lq + lq) * N + n) * 128 + lane * 4;
+  float qv[4], acc[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) qv[i] = __bfloat162float(qp[i]);
+  float m = -INFINITY, l = 0;
+  for (int j = 0; j < klen; ++j) {
+    const __nv_bfloat16* kp = k + (((long long)b * Lk + j) * N + n) * 128 + lane * 4;
+    const __nv_bfloat16* vp = v + (((long long)b * Lk + j) * N + n) * 128 + lane * 4;
+    float s = 0;
+    for (int i = 0; i < 4; ++i) s += qv[i] * __bfloat162float(kp[i]);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    s *= scale;
+    if (kls) s *= kls[j];
+    const float mn = fmaxf(m, s);
+    const float f = __expf(m - mn);
+    const float pj = __expf(s - mn);
+    l = l * f + pj;
+    const float pw = pvw ? pj * pvw[j] : pj;
+    for (int i = 0; i < 4; ++i) acc[i] = acc[i] * f + pw * __bfloat162float(vp[i]);
+    m = mn;
+  }
+  float* op = o + (((long long)b * Lq + lq) * N + n) * 128 + lane * 4;
+  for (int i = 0; i < 4; ++i) {
+    float r = klen > 0 ? acc[i] / l : 0.f;
+    if (bias && klen > 0) r += bias[n * 128 + lane * 4 + i];
+    op[i] = r;
+  }
+}
+
+static int run_fmha(int argc, char** argv) {
+  if (argc < 9) {
+    printf("fmha B Lq Lk N klen keymod iters\n");
+    return 2;
+  }
+  const int B = atoi(argv[2]), Lq = atoi(argv[3]), Lk = atoi(argv[4]), N = atoi(argv[5]);
+  const int klen = atoi(argv[6]), keymod = atoi(argv[7]), iters = atoi(argv[8]);
+  const size_t nq = (size_t)B * Lq * N * 128, nk = (size_t)B * Lk * N * 128;
+  std::vector<__nv_bfloat16> hq(nq), hk(nk), hv(nk);
+  for (auto& x : hq) x = __float2bfloat16(nrand());
+  for (auto& x : hk) x = __float2bfloat16(nrand());
+  for (auto& x : hv) x = __float2bfloat16(nrand());
+  // diagnostic input modes: 1 = K zero (uniform P: isolates the PV path), 2 = V ones (isolates
+  // normalisation), 3 = V[j][d] = (j % 128 == d) (isolates the QK^T / P path)
+  const int inmode = getenv("UVB_INMODE") ? atoi(getenv("UVB_INMODE")) : 0;
+  if (inmode == 1) for (auto& x : hk) x = __float2bfloat16(0.f);
+  if (inmode == 2) for (auto& x : hv) x = __float2bfloat16(1.f);
+  if (inmode == 3)
+    for (size_t i = 0; i < nk; ++i) hv[i] = __float2bfloat16(((i / ((size_t)N * 128)) % Lk) % 128 == i % 128 ? 1.f : 0.f);
+  __nv_bfloat16 *dq, *dk, *dv, *dout;
+  float* dref;
+  CK(cudaMalloc(&dq, nq * 2));
+  CK(cudaMalloc(&dk, nk * 2));
+  CK(cudaMalloc(&dv, nk * 2));
+  CK(cudaMalloc(&dout, nq * 2));
+  CK(cudaMalloc(&dref, nq * 4));
+  CK(cudaMemcpy(dq, hq.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dk, hk.data(), nk * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dv, hv.data(), nk * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0x7f, nq * 2));  // poison (bf16 NaN-ish pattern 0x7f7f is a large finite)
+  int* dklens = nullptr;
+  if (klen >= 0) {
+    std::vector<int> hl(B);
+    for (int b = 0; b < B; ++b) hl[b] = b == 0 ? klen : (klen * (b + 1)) % (Lk + 1);
+    CK(cudaMalloc(&dklens, B * 4));
+    CK(cudaMemcpy(dklens, hl.data(), B * 4, cudaMemcpyHostToDevice));
+  }
+  float *dkls = nullptr, *dpvw = nullptr, *dbias = nullptr;
+  if (keymod) {
+    const int Lp = (Lk + 127) / 128 * 128;
+    std::vector<float> a(Lp, 1.f), w(Lp, 1.f), bb(N * 128);
+    for (int j = 0; j < Lk; ++j) {
+      a[j] = j < Lk / 4 ? 1.3f : 1.0f;
+      w[j] = j < Lk / 4 ? 1.2f : 1.0f;
+    }
+    for (auto& x : bb) x = 0.1f * frand();
+    CK(cudaMalloc(&dkls, Lp * 4));
+    CK(cudaMalloc(&dpvw, Lp * 4));
+    CK(cudaMalloc(&dbias, N * 128 * 4));
+    CK(cudaMemcpy(dkls, a.data(), Lp * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dpvw, w.data(), Lp * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbias, bb.data(), N * 128 * 4, cudaMemcpyHostToDevice));
+  }
+  const float scale = 1.0f / sqrtf(128.f);
+  auto launch = [&]() {
+    return keymod ? uvb_xattn_fwd_bf16(dq, dk, dv, dout, dklens, dkls, dpvw, dbias, B, Lq, Lk, N,
+                                       nullptr, nullptr, nullptr, nullptr, scale, nullptr)
+                  : uvb_fmha_fwd_bf16(dq, dk, dv, dout, dklens, B, Lq, Lk, N, nullptr, nullptr,
+                                      nullptr, nullptr, scale, nullptr);
+  };
+  int rc = launch();
+  if (rc != 0) {
+    printf("FAIL launch rc=%d: %s\n", rc, uvb_last_error());
+    return 1;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("FAIL kernel: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  int status = 0;
+  const double work = (double)B * Lq * (double)Lk * N;
+  if (work <= 4e9) {
+    const long long rows = (long long)B * Lq * N;
+    naive_attn<<<(unsigned)((rows + 3) / 4), 128>>>(dq, dk, dv, dref, dklens, dkls, dpvw, dbias, B,
+                                                   Lq, Lk, N, scale);
+    CK(cudaDeviceSynchronize());
+    std::vector<__nv_bfloat16> ho(nq);
+    std::vector<float> hr(nq);
+    CK(cudaMemcpy(ho.data(), dout, nq * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hr.data(), dref, nq * 4, cudaMemcpyDeviceToHost));
+    double maxabs = 0, dot = 0, na = 0, nb = 0;
+    size_t worst = 0;
+    int nan = 0;
+    for (size_t i = 0; i < nq; ++i) {
+      const double a = __bfloat162float(ho[i]), r = hr[i];
+      if (!(a == a)) ++nan;
+      const double d = fabs(a - r);
+      if (d > maxabs) {
+        maxabs = d;
+        worst = i;
+      }
+      dot += a * r;
+      na += a * a;
+      nb += r * r;
+    }
+    const double cosv = dot / (sqrt(na) * sqrt(nb) + 1e-30);
+    const bool ok = nan == 0 && maxabs <= 2e-2 && cosv >= 0.9999;
+    printf("%s fmha B=%d Lq=%d Lk=%d N=%d klen=%d keymod=%d: max_abs=%.3e cos=%.7f nan=%d", ok ? "PASS" : "FAIL",
+           B, Lq, Lk, N, klen, keymod, maxabs, cosv, nan);
+    if (!ok) {
+      const size_t r = worst / 128;
+      printf("  worst at row=%zu (lq=%zu n=%zu) d=%zu got=%f ref=%f", r, (r / N) % Lq, r % N, worst % 128,
+             __bfloat162float(ho[worst]), hr[worst]);
+      status = 1;
+    }
+    printf("\n");
+    if (!ok) {
+      // error map by 128x? blocks to localise descriptor/layout mistakes
+      printf("  per-(qtile,dpanel) max err for b=0,n=0:\n");
+      for (int qt = 0; qt < (Lq + 127) / 128 && qt < 6; ++qt) {
+        printf("   qtile %d:", qt);
+        for (int dp = 0; dp < 8; ++dp) {
+          double mx = 0;
+          for (int r2 = qt * 128; r2 < min(Lq, qt * 128 + 128); ++r2)
+            for (int d = dp * 16; d < dp * 16 + 16; ++d) {
+              const size_t i = ((size_t)r2 * N + 0) * 128 + d;
+              mx = fmax(mx, fabs(__bfloat162float(ho[i]) - hr[i]));
+            }
+          printf(" %.2e", mx);
+        }
+        printf("\n");
+      }
+      printf("  first row got: ");
+      for (int d = 0; d < 8; ++d) printf("%.4f ", __bfloat162float(ho[d]));
+      printf("\n  first row ref: ");
+      for (int d = 0; d < 8; ++d) printf("%.4f ", hr[d]);
+      printf("\n");
+    }
+  }
+  if (iters > 0) {
+    // timing: inputs here exceed L2 only for the big shapes; flush L2 between iterations anyway
+    char* flush;
+    const size_t fb = 256u << 20;
+    CK(cudaMalloc(&flush, fb));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    double best = 1e30, tot = 0;
+    for (int i = 0; i < iters; ++i) {
+      CK(cudaMemsetAsync(flush, i, fb));
+      CK(cudaEventRecord(e0));
+      launch();
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      best = fmin(best, ms);
+      tot += ms;
+    }
+    double eff_lk = klen >= 0 ? klen : Lk;
+    const double flop = 4.0 * B * Lq * eff_lk * N * 128;
+    printf("TIME fmha B=%d Lq=%d Lk=%d N=%d: best %.3f ms (%.1f TFLOP/s)  mean %.3f ms (%.1f TFLOP/s)\n", B,
+           Lq, Lk, N, best, flop / best * 1e-9, tot / iters, flop / (tot / iters) * 1e-9);
+  }
+  return status;
+}
+
+static int run_prol(int argc, char** argv) {
+  if (argc < 8) {
+    printf("prol B L N rope dtype iters\n");
+    return 2;
+  }
+  const int B = atoi(argv[2]), L = atoi(argv[3]), N = atoi(argv[4]), rope = atoi(argv[5]);
+  const int dtype = atoi(argv[6]), iters = atoi(argv[7]);
+  const int dim = N * 128;
+  const size_t n = (size_t)B * L * dim;
+  std::vector<float> hq(n), hk(n), wq(dim), wk(dim);
+  for (auto& x : hq) x = nrand();
+  for (auto& x : hk) x = nrand() * 0.5f;
+  for (auto& x : wq) x = 1.f + 0.1f * frand();
+  for (auto& x : wk) x = 1.f + 0.1f * frand();
+  std::vector<__nv_bfloat16> bq(n), bk(n);
+  if (dtype == UVB_BF16) {
+    for (size_t i = 0; i < n; ++i) {
+      bq[i] = __float2bfloat16(hq[i]);
+      bk[i] = __float2bfloat16(hk[i]);
+      hq[i] = __bfloat162float(bq[i]);
+      hk[i] = __bfloat162float(bk[i]);
+    }
+  }
+  // grid: pick (f, h, w) with f*h*w <= L, leaving a few padding tokens when possible
+  int gf = 1, gh = 1, gw = 1;
+  {
+    gw = 13;
+    gh = 7;
+    gf = L / (gw * gh);
+    if (gf < 1) {
+      gf = 1;
+      gh = 1;
+      gw = L > 3 ? L - 3 : L;
+    }
+    if (gf > 1024) gf = 1024;
+  }
+  std::vector<float> cs(1024 * 64 * 2);
+  for (int pos = 0; pos < 1024; ++pos)
+    for (int j = 0; j < 64; ++j) {
+      double ang;
+      if (j < 22) ang = pos * pow(10000.0, -(2.0 * j) / 44.0);
+      else if (j < 43) ang = pos * pow(10000.0, -(2.0 * (j - 22)) / 42.0);
+      else ang = pos * pow(10000.0, -(2.0 * (j - 43)) / 42.0);
+      cs[(pos * 64 + j) * 2] = (float)cos(ang);
+      cs[(pos * 64 + j) * 2 + 1] = (float)sin(ang);
+    }
+  void *dq, *dk;
+  float *dwq, *dwk, *dcs;
+  __nv_bfloat16 *oq, *ok;
+  const size_t esz = dtype == UVB_BF16 ? 2 : 4;
+  CK(cudaMalloc(&dq, n * esz));
+  CK(cudaMalloc(&dk, n * esz));
+  CK(cudaMalloc(&dwq, dim * 4));
+  CK(cudaMalloc(&dwk, dim * 4));
+  CK(cudaMalloc(&dcs, cs.size() * 4));
+  CK(cudaMalloc(&oq, n * 2));
+  CK(cudaMalloc(&ok, n * 2));
+  if (dtype == UVB_BF16) {
+    CK(cudaMemcpy(dq, bq.data(), n * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk, bk.data(), n * 2, cudaMemcpyHostToDevice));
+  } else {
+    CK(cudaMemcpy(dq, hq.data(), n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk, hk.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(dwq, wq.data(), dim * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dwk, wk.data(), dim * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dcs, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<int32_t> grid(3 * B);
+  for (int b = 0; b < B; ++b) {
+    grid[3 * b] = gf;
+    grid[3 * b + 1] = gh;
+    grid[3 * b + 2] = gw;
+  }
+  const float eps = 1e-6f;
+  auto launch = [&]() {
+    return uvb_qk_norm_rope(dq, dk, dtype, dwq, dwk, rope ? dcs : nullptr, nullptr, nullptr, oq, ok, B, L,
+                            N, rope ? grid.data() : nullptr, 0, eps, N, (int64_t)L * dim, dim, 0, nullptr);
+  };
+  int rc = launch();
+  if (rc != 0) {
+    printf("FAIL launch rc=%d: %s\n", rc, uvb_last_error());
+    return 1;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("FAIL kernel: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  int status = 0;
+  {
+    std::vector<__nv_bfloat16> gq(n), gk(n);
+    CK(cudaMemcpy(gq.data(), oq, n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gk.data(), ok, n * 2, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    long long bad = 0;
+    const size_t rows = (size_t)B * L;
+    const size_t step = rows > 4096 ? rows / 4096 : 1;
+    for (size_t r = 0; r < rows; r += step) {
+      const int l = r % L;
+      for (int which = 0; which < 2; ++which) {
+        const float* x = (which ? hk.data() : hq.data()) + r * dim;
+        const float* w = which ? wk.data() : wq.data();
+        const __nv_bfloat16* g = (which ? gk.data() : gq.data()) + r * dim;
+        double ss = 0;
+        for (int i = 0; i < dim; ++i) ss += (double)x[i] * x[i];
+        const double rinv = 1.0 / sqrt(ss / dim + eps);
+        const bool rot = rope && l < gf * gh * gw;
+        const int pf = l / (gh * gw), ph = (l / gw) % gh, pw = l % gw;
+        for (int i = 0; i < dim; i += 2) {
+          double a = x[i] * rinv, b = x[i + 1] * rinv;
+          if (dtype == UVB_BF16) {
+            a = __bfloat162float(__float2bfloat16((float)a));
+            b = __bfloat162float(__float2bfloat16((float)b));
+          }
+          a *= w[i];
+          b *= w[i + 1];
+          if (rot) {
+            const int jj = (i % 128) / 2;
+            const int pos = jj < 22 ? pf : (jj < 43 ? ph : pw);
+            const double c = cs[(pos * 64 + jj) * 2], s = cs[(pos * 64 + jj) * 2 + 1];
+            const double ra = a * c - b * s, rb = a * s + b * c;
+            a = ra;
+            b = rb;
+          }
+          const double ea = fabs(__bfloat162float(g[i]) - a), eb = fabs(__bfloat162float(g[i + 1]) - b);
+          const double tol_a = 0.0079 * fabs(a) + 1e-3, tol_b = 0.0079 * fabs(b) + 1e-3;  // 2 bf16 ulp
+          if (ea > tol_a || eb > tol_b) ++bad;
+          maxerr = fmax(maxerr, fmax(ea, eb));
+        }
+      }
+    }
+    const bool okk = bad == 0;
+    printf("%s prol B=%d L=%d N=%d rope=%d dtype=%d grid=(%d,%d,%d): max_abs=%.3e bad=%lld\n", okk ? "PASS" : "FAIL",
+           B, L, N, rope, dtype, gf, gh, gw, maxerr, bad);
+    if (!okk) status = 1;
+  }
+  if (iters > 0) {
+    char* flush;
+    const size_t fb = 256u << 20;
+    CK(cudaMalloc(&flush, fb));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    double best = 1e30, tot = 0;
+    for (int i = 0; i < iters; ++i) {
+      CK(cudaMemsetAsync(flush, i, fb));
+      CK(cudaEventRecord(e0));
+      launch();
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      best = fmin(best, ms);
+      tot += ms;
+    }
+    const double bytes = 2.0 * n * (esz + 2);
+    printf("TIME prol B=%d L=%d N=%d dtype=%d: best %.3f ms (%.0f GB/s)  mean %.3f ms (%.0f GB/s)\n", B, L, N,
+           dtype, best, bytes / best * 1e-6, tot / iters, bytes / (tot / iters) * 1e-6);
+  }
+  return status;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    printf("usage: uvb_test fmha|prol ...\n");
+    return 2;
+  }
+  if (!strcmp(argv[1], "fmha")) return run_fmha(argc, argv);
+  if (!strcmp(argv[1], "prol")) return run_prol(argc, argv);
+  printf("unknown case %s\n", argv[1]);
+  return 2;
+}
