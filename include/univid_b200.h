@@ -44,7 +44,8 @@ const char* uvb_last_error(void);
  * sequence-parallel rope_apply (distributed/sequence_parallel.py:23-61).
  *
  *   q_in, k_in   [B, L, N*128] in `in_dtype` (either may be NULL to skip that tensor)
- *   wq, wk       [N*128] fp32 RMSNorm weights
+ *   wq, wk       [N*128] fp32 RMSNorm weights; NULL = no normalisation for that tensor (qk_norm=False,
+ *                nn.Identity at model.py:123-124), rotation only
  *   cos_sin      [1024, 64, 2] fp32 (cos, sin) of the reference `freqs` table (model.py:398-405),
  *                or NULL for no rotation
  *   row_scale    [L] fp32 or NULL; pre_bias [N*128] fp32 or NULL: when pre_bias != NULL the k row is

@@ -1,0 +1,123 @@
+"""Load the UNMODIFIED reference hot-path sources from /root/reference -- TEST INFRASTRUCTURE.
+
+Used only in the build container (the GPU box has no /root/reference) by
+tests/golden/make_golden.py and tests/test_oracle_vs_reference.py to pin the oracle.  Nothing is
+copied: the files are imported from where they lie (recipe: SURVEY.md sec. 8c).
+
+  * a 4-symbol stub stands in for `diffusers` (only ConfigMixin / register_to_config / ModelMixin are
+    used, model.py:6-7);
+  * models/wan/utils/modules/{attention,model}.py are loaded into a synthetic package so the
+    relative import `from .attention import flash_attention` resolves;
+  * flash_attention is routed to attention()'s torch-SDPA branch (attention.py:164-179) -- "the
+    reference's torch SDPA path" of BASELINE.json -- because the flash branch asserts CUDA;
+  * models/wan/distributed/{util,ulysses,sequence_parallel}.py load into a synthetic `wan` package;
+  * class Wan22ContextWrapper is cut out of models/model_pipeline.py with `ast` (the module itself
+    pip-installs and writes files at import time, model_pipeline.py:42-132).
+"""
+import ast
+import importlib.util
+import logging
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF_ROOT = os.environ.get("UNIVID_REFERENCE", "/root/reference")
+MODULES_DIR = os.path.join(REF_ROOT, "models/wan/utils/modules")
+DIST_DIR = os.path.join(REF_ROOT, "models/wan/distributed")
+PIPELINE = os.path.join(REF_ROOT, "models/model_pipeline.py")
+
+
+def available():
+    return os.path.isfile(os.path.join(MODULES_DIR, "model.py"))
+
+
+def _install_diffusers_stub():
+    if "diffusers" in sys.modules:
+        return
+    d = types.ModuleType("diffusers")
+    cu = types.ModuleType("diffusers.configuration_utils")
+    m = types.ModuleType("diffusers.models")
+    mu = types.ModuleType("diffusers.models.modeling_utils")
+
+    class ConfigMixin:
+        pass
+
+    def register_to_config(fn):
+        return fn
+
+    class ModelMixin(nn.Module):
+        pass
+
+    cu.ConfigMixin, cu.register_to_config, mu.ModelMixin = ConfigMixin, register_to_config, ModelMixin
+    d.configuration_utils, d.models, m.modeling_utils = cu, m, mu
+    sys.modules.update({"diffusers": d, "diffusers.configuration_utils": cu,
+                        "diffusers.models": m, "diffusers.models.modeling_utils": mu})
+
+
+def _load(pkg_name, mod_name, path):
+    full = f"{pkg_name}.{mod_name}"
+    spec = importlib.util.spec_from_file_location(full, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CACHE = {}
+
+
+def load_modules():
+    """Returns (attention_module, model_module) of the reference, SDPA-routed."""
+    if "modules" in _CACHE:
+        return _CACHE["modules"]
+    _install_diffusers_stub()
+    for name, path in (("uvref_wan", None), ("uvref_wan.modules", MODULES_DIR)):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [path] if path else []
+        sys.modules[name] = pkg
+    att = _load("uvref_wan.modules", "attention", os.path.join(MODULES_DIR, "attention.py"))
+    att.FLASH_ATTN_2_AVAILABLE = False
+    att.FLASH_ATTN_3_AVAILABLE = False
+    model = _load("uvref_wan.modules", "model", os.path.join(MODULES_DIR, "model.py"))
+
+    def flash_attention_via_sdpa(*args, version=None, **kwargs):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return att.attention(*args, **kwargs)
+
+    model.flash_attention = flash_attention_via_sdpa
+    _CACHE["modules"] = (att, model)
+    return att, model
+
+
+def load_distributed():
+    """Returns (util, ulysses, sequence_parallel) of the reference loaded under `uvref_wan`."""
+    if "dist" in _CACHE:
+        return _CACHE["dist"]
+    load_modules()
+    pkg = types.ModuleType("uvref_wan.distributed")
+    pkg.__path__ = [DIST_DIR]
+    sys.modules["uvref_wan.distributed"] = pkg
+    util = _load("uvref_wan.distributed", "util", os.path.join(DIST_DIR, "util.py"))
+    uly = _load("uvref_wan.distributed", "ulysses", os.path.join(DIST_DIR, "ulysses.py"))
+    sp = _load("uvref_wan.distributed", "sequence_parallel", os.path.join(DIST_DIR, "sequence_parallel.py"))
+    _CACHE["dist"] = (util, uly, sp)
+    return util, uly, sp
+
+
+def load_context_wrapper():
+    """The reference's Wan22ContextWrapper class, cut out of model_pipeline.py by AST."""
+    if "wrapper" in _CACHE:
+        return _CACHE["wrapper"]
+    src = open(PIPELINE).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Wan22ContextWrapper")
+    code = compile(ast.Module(body=[node], type_ignores=[]), PIPELINE, "exec")
+    ns = {"torch": torch, "logging": logging, "ContextProjector": object, "CrossAttentionConfig": object}
+    exec(code, ns)
+    _CACHE["wrapper"] = ns["Wan22ContextWrapper"]
+    return _CACHE["wrapper"]

@@ -1,0 +1,226 @@
+"""ctypes binding of libunivid_b200.so (include/univid_b200.h) and thin tensor-level wrappers.
+
+PyTorch is used for device memory and streams only; every compute call goes through the C ABI.
+There is NO fallback: if the library is missing or the device is not sm_100 the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libunivid_b200.so")
+
+EXPORTS = (
+    "uvb_version", "uvb_last_error", "uvb_qk_norm_rope", "uvb_head_scatter_bf16",
+    "uvb_fmha_fwd_bf16", "uvb_xattn_fwd_bf16",
+)
+
+UVB_BF16, UVB_F32 = 0, 1
+_c = ctypes
+_vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+_lib = None
+launch_count = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def lib():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m univid_b200.build` "
+            "(nvcc, sm_100a). univid_b200 has no fallback path.")
+    L = _c.CDLL(LIB_PATH)
+    L.uvb_version.restype = _i
+    L.uvb_last_error.restype = _c.c_char_p
+    L.uvb_qk_norm_rope.restype = _i
+    L.uvb_qk_norm_rope.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                   _vp, _i, _f, _i, _i64, _i64, _i64, _vp]
+    L.uvb_head_scatter_bf16.restype = _i
+    L.uvb_head_scatter_bf16.argtypes = [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp]
+    L.uvb_fmha_fwd_bf16.restype = _i
+    L.uvb_fmha_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp]
+    L.uvb_xattn_fwd_bf16.restype = _i
+    L.uvb_xattn_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                     _vp, _vp, _vp, _vp, _f, _vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"univid_b200 error {rc}: {lib().uvb_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("univid_b200 kernels need CUDA tensors; there is no CPU path")
+
+
+def _no_grad_only(*tensors):
+    """The hot path is forward-only: refuse to run under autograd silently."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            "univid_b200 attention kernels are forward-only; run under torch.no_grad() "
+            "(training through the DiT is outside this path's contract)")
+
+
+def _strides3(t):
+    """(batch, token, head) element strides of a [B, L, N, 128] tensor as a ctypes int64[3]."""
+    if t.stride(3) != 1:
+        raise RuntimeError("head_dim must be the contiguous dimension")
+    return (_i64 * 3)(t.stride(0), t.stride(1), t.stride(2))
+
+
+_GRID_CACHE = {}
+
+
+def _grid_array(grid_sizes):
+    key = tuple(map(tuple, grid_sizes)) if not torch.is_tensor(grid_sizes) else tuple(map(tuple, grid_sizes.tolist()))
+    arr = _GRID_CACHE.get(key)
+    if arr is None:
+        flat = [int(v) for row in key for v in row]
+        arr = (_c.c_int32 * len(flat))(*flat)
+        _GRID_CACHE[key] = arr
+    return arr, key
+
+
+def _grouped_out(o, src, groups, B, L, hpg, device):
+    """Output buffer [B, L, N, 128] (groups == 1) or [groups, B, L, N/groups, 128]; a caller-provided
+    buffer may be a strided view (e.g. one slot of a fused send buffer) as long as its two innermost
+    dimensions are dense."""
+    if src is None:
+        return None
+    shape = (B, L, hpg, 128) if groups == 1 else (groups, B, L, hpg, 128)
+    if o is None:
+        return torch.empty(shape, dtype=torch.bfloat16, device=device)
+    if tuple(o.shape) != shape or o.dtype != torch.bfloat16 or o.stride(-1) != 1 or o.stride(-2) != 128:
+        raise RuntimeError(f"bad output buffer: need bf16 {shape} with dense (head, dim)")
+    return o
+
+
+def _grouped_strides(o, groups):
+    """(out_sb, out_sl, out_sg) element strides of a buffer returned by _grouped_out."""
+    if groups == 1:
+        return o.stride(0), o.stride(1), 0
+    return o.stride(1), o.stride(2), o.stride(0)
+
+
+def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=None, tok_offset=0,
+                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None):
+    """Fused RMSNorm (+RoPE) of q and/or k: [B, L, dim] -> bf16 [B, L, N, 128] (groups == 1) or the
+    Ulysses send layout [groups, B, L, N/groups, 128].  See uvb_qk_norm_rope in the header."""
+    global launch_count
+    ref = q_in if q_in is not None else k_in
+    _require_cuda(q_in, k_in, wq, wk, cos_sin, row_scale, pre_bias)
+    _no_grad_only(q_in, k_in)
+    B, L, dim = ref.shape
+    N = num_heads
+    if dim != N * 128:
+        raise NotImplementedError(f"head_dim {dim // N} is not supported (128 only)")
+    if N % groups != 0:
+        raise ValueError(f"num_heads {N} not divisible by {groups}")
+    dt = ref.dtype
+    if dt not in (torch.bfloat16, torch.float32):
+        raise NotImplementedError(f"qk_norm_rope input dtype {dt} (bf16 / fp32 only)")
+    for t in (q_in, k_in):
+        if t is not None and (t.dtype != dt or not t.is_contiguous() or t.shape != ref.shape):
+            raise RuntimeError("q_in / k_in must be contiguous, same shape and dtype")
+    hpg = N // groups
+    q_out = _grouped_out(q_out, q_in, groups, B, L, hpg, ref.device)
+    k_out = _grouped_out(k_out, k_in, groups, B, L, hpg, ref.device)
+    strides = _grouped_strides(q_out if q_out is not None else k_out, groups)
+    if q_out is not None and k_out is not None and _grouped_strides(k_out, groups) != strides:
+        raise RuntimeError("q_out and k_out must share strides")
+    grid = None
+    if cos_sin is not None:
+        grid, key = _grid_array(grid_sizes)
+        if len(key) != B:
+            raise ValueError("grid_sizes must have one (f, h, w) row per sample")
+    f32 = lambda t: None if t is None else (t if t.dtype == torch.float32 else t.float()).contiguous()
+    wq, wk, row_scale, pre_bias = f32(wq), f32(wk), f32(row_scale), f32(pre_bias)
+    _check(lib().uvb_qk_norm_rope(
+        _ptr(q_in), _ptr(k_in), UVB_BF16 if dt == torch.bfloat16 else UVB_F32, _ptr(wq), _ptr(wk),
+        _ptr(cos_sin), _ptr(row_scale), _ptr(pre_bias), _ptr(q_out), _ptr(k_out), B, L, N,
+        None if grid is None else _c.cast(grid, _vp), int(tok_offset), float(eps), hpg,
+        strides[0], strides[1], strides[2], _stream(ref)))
+    launch_count += 1
+    return q_out, k_out
+
+
+def head_scatter(v, groups, out=None):
+    """v [B, L, N, 128] bf16 -> [groups, B, L, N/groups, 128] (Ulysses send layout)."""
+    global launch_count
+    _require_cuda(v)
+    B, L, N, D = v.shape
+    if D != 128 or v.dtype != torch.bfloat16 or not v.is_contiguous():
+        raise RuntimeError("head_scatter expects contiguous bf16 [B, L, N, 128]")
+    hpg = N // groups
+    out = _grouped_out(out, v, groups, B, L, hpg, v.device)
+    sb, sl, sg = _grouped_strides(out, groups)
+    _check(lib().uvb_head_scatter_bf16(_ptr(v), _ptr(out), B, L, N, hpg, sb, sl, sg, _stream(v)))
+    launch_count += 1
+    return out
+
+
+def _pad128(t, lk, fill=1.0):
+    if t is None:
+        return None
+    t = t.float().contiguous()
+    n = (lk + 127) // 128 * 128
+    if t.numel() == n:
+        return t
+    if t.numel() != lk:
+        raise ValueError("per-key vector must have Lk entries")
+    out = torch.full((n,), fill, dtype=torch.float32, device=t.device)
+    out[:lk] = t
+    return out
+
+
+def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale=None,
+             key_pv_weight=None, out_bias=None):
+    """softmax(q k^T * scale) v on [B, L, N, 128] bf16 tensors (any strides with contiguous head_dim).
+    k_lens: int32 CUDA tensor [B] or None.  The per-key modifiers select uvb_xattn_fwd_bf16."""
+    global launch_count
+    _require_cuda(q, k, v, k_lens, key_logit_scale, key_pv_weight, out_bias)
+    _no_grad_only(q, k, v)
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError("q, k, v must be [B, L, N, D]")
+    B, Lq, N, D = q.shape
+    Lk = k.shape[1]
+    if D != 128 or v.shape[3] != 128:
+        raise NotImplementedError(f"head_dim {D} is not supported by the sm_100a kernel (128 only)")
+    if k.shape != (B, Lk, N, D) or v.shape != (B, Lk, N, D):
+        raise NotImplementedError("grouped-query shapes (Nk != Nq) are not supported")
+    for t in (q, k, v):
+        if t.dtype != torch.bfloat16:
+            raise NotImplementedError(f"fmha_fwd computes in bf16; got {t.dtype}")
+    if out is None:
+        out = torch.empty((B, Lq, N, D), dtype=torch.bfloat16, device=q.device)
+    if k_lens is not None and (k_lens.dtype != torch.int32 or k_lens.numel() != B):
+        raise ValueError("k_lens must be int32 [B] on the device")
+    scale = float(D ** -0.5 if softmax_scale is None else softmax_scale)
+    args = (B, Lq, Lk, N, _c.cast(_strides3(q), _vp), _c.cast(_strides3(k), _vp),
+            _c.cast(_strides3(v), _vp), _c.cast(_strides3(out), _vp), scale, _stream(q))
+    if key_logit_scale is None and key_pv_weight is None and out_bias is None:
+        _check(lib().uvb_fmha_fwd_bf16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(k_lens), *args))
+    else:
+        kls, pvw = _pad128(key_logit_scale, Lk), _pad128(key_pv_weight, Lk)
+        ob = None if out_bias is None else out_bias.float().contiguous()
+        if ob is not None and ob.numel() != N * D:
+            raise ValueError("out_bias must have N*128 entries")
+        _check(lib().uvb_xattn_fwd_bf16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(k_lens), _ptr(kls),
+                                        _ptr(pvw), _ptr(ob), *args))
+    launch_count += 1
+    return out

@@ -130,16 +130,20 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
 
 template <typename InT>
 int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
-  const long long rows = static_cast<long long>(p.B) * p.L;
-  const unsigned blocks = static_cast<unsigned>((rows + uvb::kNormRopeWarps - 1) / uvb::kNormRopeWarps);
+  const long long units = 2LL * p.B * p.L;   // one warp group per (row, q|k)
   const dim3 block(uvb::kNormRopeWarps * 32);
+  auto blocks = [&](int wpr) {
+    const int per_cta = uvb::kNormRopeWarps / wpr;
+    return static_cast<unsigned>((units + per_cta - 1) / per_cta);
+  };
   const int dim = p.N * 128;
-  switch (dim) {
-    case 1536: uvb::qk_norm_rope_kernel<InT, 6><<<blocks, block, 0, stream>>>(p); break;
-    case 2048: uvb::qk_norm_rope_kernel<InT, 8><<<blocks, block, 0, stream>>>(p); break;
-    case 3072: uvb::qk_norm_rope_kernel<InT, 12><<<blocks, block, 0, stream>>>(p); break;
-    case 5120: uvb::qk_norm_rope_kernel<InT, 20><<<blocks, block, 0, stream>>>(p); break;
-    default: uvb::qk_norm_rope_kernel<InT, 0><<<blocks, block, 0, stream>>>(p); break;
+  switch (dim) {   // VPL * WPR = dim / 256
+    case 1536: uvb::qk_norm_rope_kernel<InT, 6, 1><<<blocks(1), block, 0, stream>>>(p); break;
+    case 2048: uvb::qk_norm_rope_kernel<InT, 8, 1><<<blocks(1), block, 0, stream>>>(p); break;
+    case 3072: uvb::qk_norm_rope_kernel<InT, 6, 2><<<blocks(2), block, 0, stream>>>(p); break;
+    case 4096: uvb::qk_norm_rope_kernel<InT, 8, 2><<<blocks(2), block, 0, stream>>>(p); break;
+    case 5120: uvb::qk_norm_rope_kernel<InT, 5, 4><<<blocks(4), block, 0, stream>>>(p); break;
+    default: uvb::qk_norm_rope_kernel<InT, 0, 1><<<blocks(1), block, 0, stream>>>(p); break;
   }
   UVB_CUDA(cudaGetLastError());
   return UVB_OK;
@@ -159,9 +163,8 @@ int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const flo
                      const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
                      int64_t out_sl, int64_t out_sg, void* stream) {
   if (q_in == nullptr && k_in == nullptr) return fail(UVB_ERR_INVALID, "q_in and k_in are both null");
-  if ((q_in != nullptr && (wq == nullptr || q_out == nullptr)) ||
-      (k_in != nullptr && (wk == nullptr || k_out == nullptr)))
-    return fail(UVB_ERR_INVALID, "missing weight or output pointer");
+  if ((q_in != nullptr && q_out == nullptr) || (k_in != nullptr && k_out == nullptr))
+    return fail(UVB_ERR_INVALID, "missing output pointer");
   if (B <= 0 || L <= 0 || N <= 0) return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d", B, L, N);
   if (in_dtype != UVB_BF16 && in_dtype != UVB_F32) return fail(UVB_ERR_INVALID, "bad in_dtype %d", in_dtype);
   if (hpg <= 0 || N % hpg != 0) return fail(UVB_ERR_INVALID, "hpg=%d must divide N=%d", hpg, N);

@@ -6,7 +6,7 @@
 // input dtype (`.type_as(x)`), multiplied by the fp32 weight, rotated, and rounded once to bf16
 // (the cast the reference performs at flash_attention() entry, attention.py:59-83).
 //
-// One warp owns one token row.  Lane l holds the 16-byte vectors v = l + 32*i of the row, so every
+// One warp owns one token row of q or of k.  Lane l holds the 16-byte vectors v = l + 32*i of the row, so every
 // vector of a lane has the same offset inside its head (d0 = 8*(l%16)): the lane needs just four
 // (cos, sin) pairs per token, shared by all heads and by q and k.  All loads of a row are issued
 // before the first use (VPL independent 128-bit loads per lane), the sum of squares is reduced with
@@ -82,44 +82,71 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Normalise + rotate one row held in registers and store it.
-template <typename InT, int VPL>
+// Normalise + rotate one row and store it.  The row stays PACKED in registers (VPL x 16 bytes per
+// lane for bf16) and is unpacked twice -- once for the sum of squares, once for the output -- which
+// keeps the register footprint small enough for >= 32 resident warps per SM at dim 5120.
+//
+// WPR warps cooperate on one row (lane index `lane` in [0, 32*WPR)); their partial sums of squares
+// meet in shared memory behind a named barrier private to the row.
+template <typename InT, int VPL, int WPR>
 __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const float* __restrict__ w,
                                               __nv_bfloat16* __restrict__ out_row, int hpg,
                                               long long out_sg, int dim, float eps, bool rotate,
                                               const float (&cs)[8], float rscale,
-                                              const float* __restrict__ pre_bias, int lane) {
+                                              const float* __restrict__ pre_bias, int lane,
+                                              float* red, int bar_id) {
+  constexpr int kStride = 32 * WPR;
   RowVec<InT> v[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) v[i].load(in + (lane + 32 * i) * 8);
+  for (int i = 0; i < VPL; ++i) v[i].load(in + (lane + kStride * i) * 8);
 
-  float ss = 0.f;
-  float x[VPL][8];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i].unpack(x[i]);
+  auto fetch = [&](int i, float* x) {
+    v[i].unpack(x);
     if (pre_bias != nullptr) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + 32 * i) * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + 32 * i) * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + kStride * i) * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + kStride * i) * 8) + 1);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[i][e] = RowVec<InT>::round_in(fmaf(rscale, x[i][e], bb[e]));
+      for (int e = 0; e < 8; ++e) x[e] = RowVec<InT>::round_in(fmaf(rscale, x[e], bb[e]));
     }
+  };
+
+  float ss = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ss = fmaf(x[i][e], x[i][e], ss);
+  for (int i = 0; i < VPL; ++i) {
+    float x[8];
+    fetch(i, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
   }
   ss = warp_sum(ss);
-  const float rinv = rsqrtf(ss / static_cast<float>(dim) + eps);
+  if constexpr (WPR > 1) {
+    if ((lane & 31) == 0) red[lane >> 5] = ss;
+    named_bar_sync(bar_id, kStride);
+    ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) ss += red[i];
+  }
+  // w == nullptr: qk_norm disabled (nn.Identity, model.py:123-124) -> rotation only
+  const bool normed = w != nullptr;
+  const float rinv = normed ? rsqrtf(ss / static_cast<float>(dim) + eps) : 1.0f;
 
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vec = lane + 32 * i;
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vec * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vec * 8) + 1);
-    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const int vec = lane + kStride * i;
+    float x[8];
+    fetch(i, x);
     float y[8];
+    if (normed) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vec * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vec * 8) + 1);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = RowVec<InT>::round_in(x[i][e] * rinv) * ww[e];
+      for (int e = 0; e < 8; ++e) y[e] = RowVec<InT>::round_in(x[e] * rinv) * ww[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = x[e];
+    }
     uint32_t o[4];
 #pragma unroll
     for (int pr = 0; pr < 4; ++pr) {
@@ -166,7 +193,8 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
     }
   }
   ss = warp_sum(ss);
-  const float rinv = rsqrtf(ss / static_cast<float>(dim) + eps);
+  const bool normed = w != nullptr;
+  const float rinv = normed ? rsqrtf(ss / static_cast<float>(dim) + eps) : 1.0f;
   for (int vec = lane; vec < nvec; vec += 32) {
     RowVec<InT> v;
     v.load(in + vec * 8);
@@ -180,8 +208,10 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
         a = RowVec<InT>::round_in(fmaf(rscale, a, pre_bias[vec * 8 + 2 * pr]));
         b = RowVec<InT>::round_in(fmaf(rscale, b, pre_bias[vec * 8 + 2 * pr + 1]));
       }
-      a = RowVec<InT>::round_in(a * rinv) * w[vec * 8 + 2 * pr];
-      b = RowVec<InT>::round_in(b * rinv) * w[vec * 8 + 2 * pr + 1];
+      if (normed) {
+        a = RowVec<InT>::round_in(a * rinv) * w[vec * 8 + 2 * pr];
+        b = RowVec<InT>::round_in(b * rinv) * w[vec * 8 + 2 * pr + 1];
+      }
       if (rotate) {
         const float c = cs[2 * pr], s = cs[2 * pr + 1];
         const float ra = a * c - b * s;
@@ -200,14 +230,22 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
 
 constexpr int kNormRopeWarps = 8;
 
-// VPL = dim / 256 (vectors per lane); VPL == 0 selects the generic two-pass path.
-template <typename InT, int VPL>
-__global__ void __launch_bounds__(kNormRopeWarps * 32)
+// One group of WPR warps per (token row, tensor): even groups take q, odd groups k, so the groups of a
+// token sit next to each other and share the token's (cos, sin) lines in L1.
+// VPL * WPR = dim / 256 (16-byte vectors per lane); VPL == 0 selects the generic two-pass path.
+template <typename InT, int VPL, int WPR>
+__global__ void __launch_bounds__(kNormRopeWarps * 32, sizeof(InT) == 2 ? 3 : 2)
 qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[kNormRopeWarps];
   const int warp = threadIdx.x >> 5;
-  const long long row = static_cast<long long>(blockIdx.x) * kNormRopeWarps + warp;
+  const int group = warp / WPR;                       // row group inside the CTA
+  const int lane = threadIdx.x - group * (32 * WPR);  // lane inside the group
+  const long long unit = static_cast<long long>(blockIdx.x) * (kNormRopeWarps / WPR) + group;
+  const long long row = unit >> 1;
+  const bool is_k = (unit & 1) != 0;
   if (row >= static_cast<long long>(p.B) * p.L) return;
+  const InT* src = static_cast<const InT*>(is_k ? p.k_in : p.q_in);
+  if (src == nullptr) return;
   const int b = static_cast<int>(row / p.L);
   const int l = static_cast<int>(row % p.L);
   const int dim = p.N * 128;
@@ -239,23 +277,16 @@ qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
 
   const long long in_off = row * dim;
   const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
-  const InT* q_in = static_cast<const InT*>(p.q_in);
-  const InT* k_in = static_cast<const InT*>(p.k_in);
-  const float rscale = p.row_scale != nullptr ? p.row_scale[l] : 1.0f;
+  const float* w = is_k ? p.wk : p.wq;
+  __nv_bfloat16* dst = (is_k ? p.k_out : p.q_out) + out_off;
+  const float* pre_bias = is_k ? p.pre_bias : nullptr;
+  const float rscale = (is_k && p.row_scale != nullptr) ? p.row_scale[l] : 1.0f;
   if constexpr (VPL > 0) {
-    if (q_in != nullptr)
-      norm_rope_row<InT, VPL>(q_in + in_off, p.wq, p.q_out + out_off, p.hpg, p.out_sg, dim, p.eps,
-                              rotate, cs, 1.0f, nullptr, lane);
-    if (k_in != nullptr)
-      norm_rope_row<InT, VPL>(k_in + in_off, p.wk, p.k_out + out_off, p.hpg, p.out_sg, dim, p.eps,
-                              rotate, cs, rscale, p.pre_bias, lane);
+    norm_rope_row<InT, VPL, WPR>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
+                                 rscale, pre_bias, lane, red + group * WPR, 1 + group);
   } else {
-    if (q_in != nullptr)
-      norm_rope_row_generic<InT>(q_in + in_off, p.wq, p.q_out + out_off, p.hpg, p.out_sg, dim,
-                                 p.eps, rotate, cs, 1.0f, nullptr, lane);
-    if (k_in != nullptr)
-      norm_rope_row_generic<InT>(k_in + in_off, p.wk, p.k_out + out_off, p.hpg, p.out_sg, dim,
-                                 p.eps, rotate, cs, rscale, p.pre_bias, lane);
+    norm_rope_row_generic<InT>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs, rscale,
+                               pre_bias, lane);
   }
 }
 

@@ -359,7 +359,10 @@ static int run_prol(int argc, char** argv) {
             b = rb;
           }
           const double ea = fabs(__bfloat162float(g[i]) - a), eb = fabs(__bfloat162float(g[i + 1]) - b);
-          const double tol_a = 0.0079 * fabs(a) + 1e-3, tol_b = 0.0079 * fabs(b) + 1e-3;  // 2 bf16 ulp
+          // 2 bf16 ulp of the pair magnitude: a 1-ulp flip of the intermediate `.type_as` rounding
+          // of either input moves BOTH rotated outputs by up to that much
+          const double mag = fmax(fmax(fabs(a), fabs(b)), fmax(fabs(x[i] * rinv * w[i]), fabs(x[i + 1] * rinv * w[i + 1])));
+          const double tol_a = 0.0079 * mag + 1e-3, tol_b = tol_a;
           if (ea > tol_a || eb > tol_b) ++bad;
           maxerr = fmax(maxerr, fmax(ea, eb));
         }

@@ -1,0 +1,89 @@
+"""Drop-in for models/wan/distributed/sequence_parallel.py: the functions the reference binds onto
+WanSelfAttention / WanModel instances with types.MethodType when use_sp=True
+(textimage2video.py:143-147).
+
+sp_attn_forward is the multi-GPU hot path: the fused prologue kernel normalises, rotates (with the
+rank's token offset) and stores q and k straight into the Ulysses send layout; v is scattered by a
+copy kernel; three all-to-alls, the attention kernel on [B, L, N/p, 128], one all-to-all back.
+"""
+import torch
+
+from ... import _ext
+from ..modules.model import _cos_sin_table, sinusoidal_embedding_1d  # noqa: F401
+from .ulysses import attend_exchanged, distributed_attention  # noqa: F401
+from .util import gather_forward, get_rank, get_world_size
+
+
+def pad_freqs(original_tensor, target_len):
+    """Pad a [S, 1, C] rotation table with ones (identity rotation) up to target_len (sequence_parallel.py:10-20)."""
+    seq_len, s1, s2 = original_tensor.shape
+    pad = original_tensor.new_ones(target_len - seq_len, s1, s2)
+    return torch.cat([original_tensor, pad], dim=0)
+
+
+@torch.amp.autocast('cuda', enabled=False)
+def rope_apply(x, grid_sizes, freqs):
+    """Rank-local RoPE with the reference semantics (sequence_parallel.py:23-61): x [B, s, N, D] holds
+    tokens [rank*s, (rank+1)*s) of the sequence; positions beyond f*h*w rotate by 1+0j.  Stand-alone,
+    PyTorch ops in float64; sp_attn_forward uses the fused kernel instead."""
+    s, half = x.size(1), x.size(3) // 2
+    widths = [half - 2 * (half // 3), half // 3, half // 3]
+    f_t, f_h, f_w = freqs.split(widths, dim=1)
+    rank, world = get_rank(), get_world_size()
+    out = x.to(torch.float64).clone()
+    for i, (f, h, w) in enumerate(grid_sizes.tolist()):
+        t = torch.arange(f * h * w, device=freqs.device)
+        rot = torch.cat([f_t[t // (h * w)], f_h[(t // w) % h], f_w[t % w]], dim=1).unsqueeze(1)
+        if rot.size(0) < s * world:
+            rot = pad_freqs(rot, s * world)
+        rot = rot[rank * s:(rank + 1) * s].to(x.device)
+        c, sn = rot.real, rot.imag
+        xe, xo = out[i, :s, :, 0::2].clone(), out[i, :s, :, 1::2].clone()
+        out[i, :s, :, 0::2] = xe * c - xo * sn
+        out[i, :s, :, 1::2] = xe * sn + xo * c
+    return out.float()
+
+
+def sp_dit_forward(
+    self,
+    x,
+    t,
+    context,
+    seq_len,
+    y=None,
+):
+    """WanModel.forward with the token dimension sharded over the ranks (sequence_parallel.py:64-144):
+    embeddings are computed on every rank, each rank keeps its chunk of the tokens through the blocks
+    and the head, and the outputs are all-gathered before unpatchify."""
+    x, e, kwargs = self.embed(x, t, context, seq_len, y)
+    world, rank = get_world_size(), get_rank()
+    x = torch.chunk(x, world, dim=1)[rank]
+    if e.size(1) > 1:   # per-token timesteps: shard the modulation with the tokens
+        e = torch.chunk(e, world, dim=1)[rank]
+        kwargs['e'] = torch.chunk(kwargs['e'], world, dim=1)[rank]
+    for block in self.blocks:
+        x = block(x, **kwargs)
+    x = self.head(x, e)
+    x = gather_forward(x, dim=1)
+    x = self.unpatchify(x, kwargs['grid_sizes'])
+    return [u.float() for u in x]
+
+
+def sp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16):
+    """WanSelfAttention.forward on a token shard x [B, L/p, C] (sequence_parallel.py:147-176)."""
+    if dtype != torch.bfloat16:
+        raise NotImplementedError('univid_b200 sequence-parallel attention computes in bfloat16 only')
+    b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
+    world, rank = get_world_size(), get_rank()
+    if world == 1:
+        return type(self).forward(self, x, seq_lens, grid_sizes, freqs)
+    if n % world != 0:
+        raise ValueError(f'{n} heads cannot be split over {world} ranks')
+    q_send, k_send = self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes,
+                                    tok_offset=rank * s, groups=world)
+    v = self.v(x).view(b, s, n, d)
+    if v.dtype != torch.bfloat16:
+        v = v.to(torch.bfloat16)
+    v_send = _ext.head_scatter(v.contiguous(), world)
+    x = attend_exchanged(q_send, k_send, v_send, seq_lens)
+    return self._out_proj(x)

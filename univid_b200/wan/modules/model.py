@@ -1,0 +1,437 @@
+"""Drop-in for the attention part of models/wan/utils/modules/model.py (logical path
+wan/modules/model.py) backed by the sm_100a kernels of libunivid_b200.so.
+
+Hot path (BASELINE.json north_star), reference lines in brackets:
+  WanRMSNorm            [model.py:69-85]   q/k norm over the full model width
+  rope_params/rope_apply[model.py:27-66]   3-D rotary embedding, fp64 in the reference
+  WanSelfAttention      [model.py:101-155] fused norm+rope prologue kernel -> tcgen05 flash attention
+  WanCrossAttention     [model.py:158-180] norm-only prologue -> flash attention over 512 context keys;
+                                           opt-in fused text weighting (model_pipeline.py:1756-1803)
+Everything else in this file (WanLayerNorm, WanAttentionBlock, Head, WanModel) is the plain-PyTorch
+harness around the hot path that the denoise-step measurement needs; it
+keeps the reference's parameter names so reference checkpoints load, and its module/attribute names
+so the product's monkey patches (Wan22ContextWrapper, sp_attn_forward, LoRA targets) keep working.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import _ext
+from .attention import _k_lens_arg, flash_attention
+
+__all__ = ['WanModel']
+
+
+def sinusoidal_embedding_1d(dim, position):
+    """[len(position), dim] float64: cos(p * 10000^(-i/half)) | sin(...)  (model.py:14-24)."""
+    assert dim % 2 == 0
+    half = dim // 2
+    pos = position.to(torch.float64)
+    inv = torch.pow(10000, -torch.arange(half, dtype=torch.float64, device=pos.device) / half)
+    ang = pos[:, None] * inv[None, :]
+    return torch.cat([ang.cos(), ang.sin()], dim=1)
+
+
+@torch.amp.autocast('cuda', enabled=False)
+def rope_params(max_seq_len, dim, theta=10000):
+    """complex128 [max_seq_len, dim/2] table exp(i * p * theta^(-2j/dim))  (model.py:27-35)."""
+    assert dim % 2 == 0
+    expo = torch.arange(0, dim, 2, dtype=torch.float64) / dim
+    ang = torch.outer(torch.arange(max_seq_len, dtype=torch.float64), 1.0 / torch.pow(theta, expo))
+    return torch.polar(torch.ones_like(ang), ang)
+
+
+_COS_SIN_CACHE = {}
+
+
+def _cos_sin_table(freqs, device):
+    """fp32 [1024, 64, 2] (cos, sin) device table for the prologue kernel, cached per freqs tensor."""
+    key = (freqs.data_ptr(), tuple(freqs.shape), str(device))
+    tab = _COS_SIN_CACHE.get(key)
+    if tab is None:
+        if freqs.dim() != 2 or freqs.shape[1] != 64 or not freqs.is_complex():
+            raise NotImplementedError('the RoPE kernel expects the [M, 64] complex table of head_dim 128')
+        f = freqs
+        if f.shape[0] < 1024:
+            f = torch.cat([f, torch.ones(1024 - f.shape[0], 64, dtype=f.dtype, device=f.device)])
+        tab = torch.stack([f.real[:1024], f.imag[:1024]], dim=-1).to(device=device, dtype=torch.float32).contiguous()
+        if len(_COS_SIN_CACHE) > 16:
+            _COS_SIN_CACHE.clear()
+        _COS_SIN_CACHE[key] = tab
+    return tab
+
+
+@torch.amp.autocast('cuda', enabled=False)
+def rope_apply(x, grid_sizes, freqs):
+    """Stand-alone 3-D RoPE with the reference's semantics (model.py:38-66): x [B, L, N, D] any float
+    dtype, rotation evaluated in float64, tokens >= f*h*w untouched, fp32 result.  API-compatibility
+    entry point (model_animate.py and sequence_parallel.py import it); WanSelfAttention below does
+    not call it -- its rotation is fused into the prologue kernel."""
+    half = x.size(3) // 2
+    widths = [half - 2 * (half // 3), half // 3, half // 3]
+    f_t, f_h, f_w = freqs.split(widths, dim=1)
+    out = x.to(torch.float64).clone()
+    for i, (f, h, w) in enumerate(grid_sizes.tolist()):
+        n_tok = f * h * w
+        t = torch.arange(n_tok, device=x.device)
+        rot = torch.cat([f_t[t // (h * w)], f_h[(t // w) % h], f_w[t % w]], dim=1).to(x.device)
+        c, s = rot.real[:, None, :], rot.imag[:, None, :]
+        xe, xo = out[i, :n_tok, :, 0::2].clone(), out[i, :n_tok, :, 1::2].clone()
+        out[i, :n_tok, :, 0::2] = xe * c - xo * s
+        out[i, :n_tok, :, 1::2] = xe * s + xo * c
+    return out.float()
+
+
+class WanRMSNorm(nn.Module):
+    """y = (x.float() * rsqrt(mean(x^2) + eps)).type_as(x) * weight  (model.py:69-85).  Used stand-alone
+    this module runs as PyTorch ops; inside WanSelfAttention / WanCrossAttention only `.weight` and
+    `.eps` are read and the normalisation happens in the fused prologue kernel."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        xf = x.float()
+        return (xf * torch.rsqrt(xf.square().mean(dim=-1, keepdim=True) + self.eps)).type_as(x) * self.weight
+
+
+class WanLayerNorm(nn.LayerNorm):
+    """fp32 LayerNorm returning the input dtype (model.py:88-98)."""
+
+    def __init__(self, dim, eps=1e-6, elementwise_affine=False):
+        super().__init__(dim, elementwise_affine=elementwise_affine, eps=eps)
+
+    def forward(self, x):
+        return super().forward(x.float()).type_as(x)
+
+
+def _norm_weight(norm):
+    """(weight, eps, pre) for a q/k norm module: a WanRMSNorm is folded into the kernel; nn.Identity
+    (qk_norm=False, model.py:123-124) means rotation only; anything else is applied as a module first."""
+    if isinstance(norm, WanRMSNorm):
+        return norm.weight, norm.eps, None
+    if isinstance(norm, nn.Identity):
+        return None, 0.0, None
+    return None, 0.0, norm
+
+
+def _proj_for_kernel(t):
+    if t.dtype not in (torch.bfloat16, torch.float32):
+        raise NotImplementedError(f'univid_b200 attention runs on bf16/fp32 projections, got {t.dtype}')
+    return t.contiguous()
+
+
+class WanSelfAttention(nn.Module):
+
+    def __init__(self,
+                 dim,
+                 num_heads,
+                 window_size=(-1, -1),
+                 qk_norm=True,
+                 eps=1e-6):
+        assert dim % num_heads == 0
+        super().__init__()
+        self.dim = dim
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.eps = eps
+
+        self.q = nn.Linear(dim, dim)
+        self.k = nn.Linear(dim, dim)
+        self.v = nn.Linear(dim, dim)
+        self.o = nn.Linear(dim, dim)
+        self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+        self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+
+    def _prologue(self, q_lin, k_lin, cos_sin, grid_sizes, tok_offset=0, groups=1):
+        """norm_q/norm_k (+RoPE) -> bf16 [B, L, N, 128] (or the Ulysses send layout when groups > 1)."""
+        wq, eps_q, pre_q = _norm_weight(self.norm_q)
+        wk, eps_k, pre_k = _norm_weight(self.norm_k)
+        if pre_q is not None:
+            q_lin = pre_q(q_lin)
+        if pre_k is not None:
+            k_lin = pre_k(k_lin)
+        q_lin = None if q_lin is None else _proj_for_kernel(q_lin)
+        k_lin = None if k_lin is None else _proj_for_kernel(k_lin)
+        eps = eps_q if wq is not None else eps_k
+        return _ext.qk_norm_rope(q_lin, k_lin, wq, wk, eps, self.num_heads, cos_sin=cos_sin,
+                                 grid_sizes=grid_sizes, tok_offset=tok_offset, groups=groups)
+
+    def _out_proj(self, x):
+        """o(x.flatten(2)); outside autocast the bf16 attention result is cast to the weight dtype
+        (the reference hands fp32 to `o`, attention.py:130 -- the values are identical)."""
+        x = x.flatten(2)
+        if not torch.is_autocast_enabled():
+            w = getattr(self.o, 'weight', None)
+            if w is not None and w.dtype != x.dtype:
+                x = x.to(w.dtype)
+        return self.o(x)
+
+    def forward(self, x, seq_lens, grid_sizes, freqs):
+        r"""
+        Args:
+            x(Tensor): Shape [B, L, C]
+            seq_lens(Tensor): Shape [B], valid tokens per sample (keys beyond are masked)
+            grid_sizes(Tensor): Shape [B, 3], (F, H, W) token grid per sample
+            freqs(Tensor): complex RoPE table [1024, C / num_heads / 2]
+        """
+        if tuple(self.window_size) != (-1, -1):
+            raise NotImplementedError('univid_b200: sliding-window self-attention is not implemented')
+        b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
+        q, k = self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes)
+        v = self.v(x).view(b, s, n, d)
+        if v.dtype != torch.bfloat16:
+            v = v.to(torch.bfloat16)
+        x = _ext.fmha_fwd(q, k, v, k_lens=_k_lens_arg(seq_lens, b, s, x.device))
+        return self._out_proj(x)
+
+
+class WanCrossAttention(WanSelfAttention):
+
+    def forward(self, x, context, context_lens, text_weight=1.0, text_len=0):
+        r"""
+        Args:
+            x(Tensor): Shape [B, L1, C]
+            context(Tensor): Shape [B, L2, C]
+            context_lens(Tensor): Shape [B] or None
+            text_weight, text_len: opt-in FUSED form of UniVid's dynamic text weighting: equivalent to
+                calling with context[:, :text_len] * text_weight (what Wan22ContextWrapper's hook does,
+                model_pipeline.py:1789-1797) but the scaled context is never materialised: the weight is
+                folded into the k-norm prologue and applied to the probabilities inside the attention
+                kernel.  With the defaults this is the reference forward (model.py:160-180); a context
+                pre-scaled by the reference hook goes through that default path unchanged.
+        """
+        b, n, d = x.size(0), self.num_heads, self.head_dim
+        fused = text_weight != 1.0 and text_len > 0
+        q, _ = self._prologue(self.q(x), None, None, None)
+        if not fused:
+            _, k = self._prologue(None, self.k(context), None, None)
+            v = self.v(context).view(b, -1, n, d)
+            if v.dtype != torch.bfloat16:
+                v = v.to(torch.bfloat16)
+            lk = k.size(1)
+            x = _ext.fmha_fwd(q, k, v, k_lens=_k_lens_arg(context_lens, b, lk, x.device))
+            return self._out_proj(x)
+
+        # k(w*c) = w*(k(c) - b_k) + b_k and v(w*c) = w*(v(c) - b_v) + b_v: run the projections on the
+        # unscaled context (as modules, so LoRA wrappers stay in the loop) and recover the biases as
+        # the image of zero.
+        lk = context.size(1)
+        zero = context.new_zeros(1, 1, context.size(-1))
+        b_k, b_v = self.k(zero).flatten().float(), self.v(zero).flatten().float()
+        k_lin = (self.k(context).float() - b_k).to(torch.bfloat16)
+        v_lin = (self.v(context).float() - b_v).to(torch.bfloat16).view(b, lk, n, d)
+        w_vec = torch.ones(lk, dtype=torch.float32, device=x.device)
+        w_vec[:text_len] = float(text_weight)
+        wk, eps_k, pre_k = _norm_weight(self.norm_k)
+        if pre_k is not None:
+            raise NotImplementedError('fused text weighting needs a WanRMSNorm or Identity norm_k')
+        _, k = _ext.qk_norm_rope(None, k_lin.contiguous(), None, wk, eps_k, n, row_scale=w_vec, pre_bias=b_k)
+        x = _ext.fmha_fwd(q, k, v_lin, k_lens=_k_lens_arg(context_lens, b, lk, x.device),
+                          key_pv_weight=w_vec, out_bias=b_v)
+        return self._out_proj(x)
+
+
+class WanAttentionBlock(nn.Module):
+    """DiT block: adaLN-modulated self-attention, cross-attention, FFN (model.py:183-259)."""
+
+    def __init__(self,
+                 dim,
+                 ffn_dim,
+                 num_heads,
+                 window_size=(-1, -1),
+                 qk_norm=True,
+                 cross_attn_norm=False,
+                 eps=1e-6):
+        super().__init__()
+        self.dim = dim
+        self.ffn_dim = ffn_dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.cross_attn_norm = cross_attn_norm
+        self.eps = eps
+
+        self.norm1 = WanLayerNorm(dim, eps)
+        self.self_attn = WanSelfAttention(dim, num_heads, window_size, qk_norm, eps)
+        self.norm3 = WanLayerNorm(dim, eps, elementwise_affine=True) if cross_attn_norm else nn.Identity()
+        self.cross_attn = WanCrossAttention(dim, num_heads, (-1, -1), qk_norm, eps)
+        self.norm2 = WanLayerNorm(dim, eps)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn_dim), nn.GELU(approximate='tanh'), nn.Linear(ffn_dim, dim))
+        self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim**0.5)
+
+    def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens):
+        r"""
+        x [B, L, C]; e [B, L or 1, 6, C] fp32 time modulation (a singleton token axis broadcasts, which is
+        what a scalar timestep expanded over the sequence amounts to, model.py:460-468).
+        """
+        assert e.dtype == torch.float32
+        with torch.amp.autocast('cuda', dtype=torch.float32):
+            shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = (
+                u.squeeze(2) for u in (self.modulation.unsqueeze(0) + e).chunk(6, dim=2))
+
+        y = self.self_attn(torch.addcmul(shift_a, self.norm1(x).float(), 1 + scale_a), seq_lens, grid_sizes, freqs)
+        with torch.amp.autocast('cuda', dtype=torch.float32):
+            x = x + y * gate_a
+        x = x + self.cross_attn(self.norm3(x), context, context_lens)
+        y = self.ffn(torch.addcmul(shift_f, self.norm2(x).float(), 1 + scale_f))
+        with torch.amp.autocast('cuda', dtype=torch.float32):
+            x = x + y * gate_f
+        return x
+
+
+class Head(nn.Module):
+    """Final modulated LayerNorm + projection to patch pixels (model.py:262-290)."""
+
+    def __init__(self, dim, out_dim, patch_size, eps=1e-6):
+        super().__init__()
+        self.dim = dim
+        self.out_dim = out_dim
+        self.patch_size = patch_size
+        self.eps = eps
+        self.norm = WanLayerNorm(dim, eps)
+        self.head = nn.Linear(dim, math.prod(patch_size) * out_dim)
+        self.modulation = nn.Parameter(torch.randn(1, 2, dim) / dim**0.5)
+
+    def forward(self, x, e):
+        assert e.dtype == torch.float32
+        with torch.amp.autocast('cuda', dtype=torch.float32):
+            shift, scale = (u.squeeze(2) for u in (self.modulation.unsqueeze(0) + e.unsqueeze(2)).chunk(2, dim=2))
+            return self.head(self.norm(x) * (1 + scale) + shift)
+
+
+class WanModel(nn.Module):
+    """Wan DiT backbone (model.py:293-546) as a plain nn.Module harness around the attention hot path.
+    Same constructor arguments, parameter names and forward signature as the reference; the reference's
+    diffusers mixins (config registration, from_pretrained) are not reproduced."""
+
+    def __init__(self,
+                 model_type='t2v',
+                 patch_size=(1, 2, 2),
+                 text_len=512,
+                 in_dim=16,
+                 dim=2048,
+                 ffn_dim=8192,
+                 freq_dim=256,
+                 text_dim=4096,
+                 out_dim=16,
+                 num_heads=16,
+                 num_layers=32,
+                 window_size=(-1, -1),
+                 qk_norm=True,
+                 cross_attn_norm=True,
+                 eps=1e-6):
+        super().__init__()
+        assert model_type in ['t2v', 'i2v', 'ti2v', 's2v']
+        self.model_type = model_type
+        self.patch_size = patch_size
+        self.text_len = text_len
+        self.in_dim = in_dim
+        self.dim = dim
+        self.ffn_dim = ffn_dim
+        self.freq_dim = freq_dim
+        self.text_dim = text_dim
+        self.out_dim = out_dim
+        self.num_heads = num_heads
+        self.num_layers = num_layers
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.cross_attn_norm = cross_attn_norm
+        self.eps = eps
+
+        self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=patch_size, stride=patch_size)
+        self.text_embedding = nn.Sequential(nn.Linear(text_dim, dim), nn.GELU(approximate='tanh'), nn.Linear(dim, dim))
+        self.time_embedding = nn.Sequential(nn.Linear(freq_dim, dim), nn.SiLU(), nn.Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.SiLU(), nn.Linear(dim, dim * 6))
+        self.blocks = nn.ModuleList([
+            WanAttentionBlock(dim, ffn_dim, num_heads, window_size, qk_norm, cross_attn_norm, eps)
+            for _ in range(num_layers)
+        ])
+        self.head = Head(dim, out_dim, patch_size, eps)
+
+        # plain attribute, not a buffer, so .to(dtype) leaves the complex128 table alone (model.py:397)
+        assert (dim % num_heads) == 0 and (dim // num_heads) % 2 == 0
+        d = dim // num_heads
+        self.freqs = torch.cat([
+            rope_params(1024, d - 4 * (d // 6)),
+            rope_params(1024, 2 * (d // 6)),
+            rope_params(1024, 2 * (d // 6)),
+        ], dim=1)
+        self.init_weights()
+
+    def embed(self, x, t, context, seq_len, y=None):
+        """Everything before the blocks (model.py:436-487): patchify + pad, time / text embeddings.
+        Returns (x [B, seq_len, C], e, kwargs for the blocks)."""
+        if self.model_type == 'i2v':
+            assert y is not None
+        device = self.patch_embedding.weight.device
+        if self.freqs.device != device:
+            self.freqs = self.freqs.to(device)
+        if y is not None:
+            x = [torch.cat([u, v], dim=0) for u, v in zip(x, y)]
+
+        x = [self.patch_embedding(u.unsqueeze(0)) for u in x]
+        grid_sizes = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in x])
+        x = [u.flatten(2).transpose(1, 2) for u in x]
+        seq_lens = torch.tensor([u.size(1) for u in x], dtype=torch.long)
+        assert seq_lens.max() <= seq_len
+        x = torch.cat([torch.cat([u, u.new_zeros(1, seq_len - u.size(1), u.size(2))], dim=1) for u in x])
+
+        # a [B] timestep is one value per sample: keep a singleton token axis and let it broadcast instead
+        # of materialising seq_len identical rows (the reference expands, model.py:460-461; same values)
+        if t.dim() == 1:
+            t = t.unsqueeze(1)
+        with torch.amp.autocast('cuda', dtype=torch.float32):
+            bt, lt = t.shape
+            e = self.time_embedding(sinusoidal_embedding_1d(self.freq_dim, t.flatten()).unflatten(0, (bt, lt)).float())
+            e0 = self.time_projection(e).unflatten(2, (6, self.dim))
+            assert e.dtype == torch.float32 and e0.dtype == torch.float32
+
+        context = self.text_embedding(
+            torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
+        kwargs = dict(e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=context,
+                      context_lens=None)
+        return x, e, kwargs
+
+    def forward(self, x, t, context, seq_len, y=None):
+        r"""
+        x: list of [C_in, F, H, W] latents; t: [B] (or [B, seq_len]) timesteps; context: list of [L, C]
+        text embeddings; seq_len: padded token count.  Returns a list of [C_out, F, H, W] tensors.
+        """
+        x, e, kwargs = self.embed(x, t, context, seq_len, y)
+        for block in self.blocks:
+            x = block(x, **kwargs)
+        x = self.head(x, e)
+        x = self.unpatchify(x, kwargs['grid_sizes'])
+        return [u.float() for u in x]
+
+    def unpatchify(self, x, grid_sizes):
+        """[L, C_out * prod(patch)] token rows back to [C_out, F*pf, H*ph, W*pw] (model.py:499-522)."""
+        c = self.out_dim
+        out = []
+        for u, v in zip(x, grid_sizes.tolist()):
+            u = u[:math.prod(v)].view(*v, *self.patch_size, c)
+            u = torch.einsum('fhwpqrc->cfphqwr', u)
+            out.append(u.reshape(c, *[i * j for i, j in zip(v, self.patch_size)]))
+        return out
+
+    def init_weights(self):
+        """Xavier-uniform linears with zero bias; N(0, .02) text/time embeddings; zero output head
+        (model.py:524-546)."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        nn.init.xavier_uniform_(self.patch_embedding.weight.flatten(1))
+        for seq in (self.text_embedding, self.time_embedding):
+            for m in seq.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.normal_(m.weight, std=.02)
+        nn.init.zeros_(self.head.head.weight)
