@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the Wan DiT attention hot path (BASELINE.json metric) -- prints ONE JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1.3B|14B]
+    torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL; Ulysses head sharding)
+
+A *step* is the attention stack of one DiT forward (one denoise step) of the named config: for each of
+the model's layers, q/k WanRMSNorm + 3-D RoPE, self-attention over all video tokens, and the 512-key
+cross-attention.  `value` is attention TFLOP/s with the layer inputs (q/k/v projections) resident in
+HBM, measured over the kernels of this repo only; `e2e` is the same FLOPs divided by the time of the
+public module API (WanSelfAttention / WanCrossAttention .forward, q/k/v/o linears included) fed from
+pinned HOST memory with the result read back to the host every step.  `denoise_step_ms` additionally
+times the full WanModel.forward harness (all blocks with PyTorch linears / FFN) once.
+
+--impl reference times the reference's CPU path for the same metric: the oracle port of the reference
+modules (oracle/wan_attention_oracle.py; the reference itself is Python and cannot travel to the GPU
+box) on the host cores, on a bounded sample of the workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1..3]: Wan2.1-T2V-1.3B, 81 frames 480x832 -> token grid (21, 30, 52)
+    "1.3B": dict(name="Wan2.1-T2V-1.3B denoise step, 81f 480x832", dim=1536, heads=12, layers=30, ffn=8960,
+                 grid=(21, 30, 52), text_len=512),
+    # BASELINE.json configs[3]: Wan2.1-T2V-14B, 81 frames 720x1280 -> token grid (21, 45, 80)
+    "14B": dict(name="Wan2.1-T2V-14B denoise step, 81f 720x1280", dim=5120, heads=40, layers=40, ffn=13824,
+                grid=(21, 45, 80), text_len=512),
+}
+
+
+def flops_per_layer(L, heads, text_len):
+    f_self = 4.0 * L * L * heads * 128
+    f_cross = 4.0 * L * text_len * heads * 128
+    return f_self, f_cross
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(source="measured", tflops_burst=p["bf16_tflops"],
+                    tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), hbm_gbs=p["hbm_gbs"])
+    return dict(source="fallback", tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                              ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []      # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg, seconds_budget, steps, warmup):
+    """Times oracle.self_attention + oracle.cross_attention (bf16 autocast-equivalent, torch-SDPA route:
+    what the reference runs on CPU) for ONE layer on a bounded token sample.  Returns (tflops, ms_per_step,
+    sample description, threads)."""
+    from oracle import wan_attention_oracle as orc
+    dim, heads, text_len = cfg["dim"], cfg["heads"], cfg["text_len"]
+    f, h, w = cfg["grid"]
+    threads = torch.get_num_threads()
+    # probe at a small size to choose the largest frame count that fits the time budget
+    g = torch.Generator().manual_seed(0)
+    prm_s = orc.init_attention_params(dim, g)
+    prm_c = orc.init_attention_params(dim, g)
+    freqs = orc.make_freqs(128)
+
+    def run(frames):
+        L = frames * h * w
+        x = torch.randn(1, L, dim, generator=g).to(torch.bfloat16)
+        ctx = torch.randn(1, text_len, dim, generator=g).to(torch.bfloat16)
+        gs, sl = torch.tensor([[frames, h, w]]), torch.tensor([L])
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.self_attention(x, prm_s, sl, gs, freqs, heads, 1e-6, bf16=True)
+            orc.cross_attention(x, ctx, prm_c, heads, None, 1e-6, bf16=True)
+        return time.perf_counter() - t0, L
+
+    t_probe, l_probe = run(1)
+    per_step_budget = seconds_budget / max(steps + warmup, 1)
+    frames = 1
+    for cand in range(f, 0, -1):       # self-attention time grows ~quadratically with the token count
+        est = t_probe * (cand * h * w / l_probe) ** 2
+        if est <= per_step_budget:
+            frames = cand
+            break
+    for _ in range(warmup):
+        run(frames)
+    times = []
+    for _ in range(steps):
+        t, L = run(frames)
+        times.append(t)
+    L = frames * h * w
+    fs, fc = flops_per_layer(L, heads, text_len)
+    sec = sum(times) / len(times)
+    sample = (f"1 of {cfg['layers']} layers (WanSelfAttention + WanCrossAttention incl. q/k/v/o linears), "
+              f"{frames} of {f} latent frames = {L} of {f * h * w} video tokens, CPU bf16 torch-SDPA route")
+    return (fs + fc) / sec * 1e-12, sec * 1e3, sample, threads
+
+
+def run_reference_arm(args, cfg_key):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[cfg_key]
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    tflops, ms, sample, threads = cpu_reference_rate(cfg, 150.0, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "dit_attention_tflops", "value": tflops, "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": cfg["name"] + " -- attention stack", "sample": sample},
+        "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------
+def run_native_arm(args, cfg_key):
+    import torch.distributed as dist
+    from univid_b200 import _ext
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    sp = importlib.import_module("univid_b200.wan.distributed.sequence_parallel")
+    uly = importlib.import_module("univid_b200.wan.distributed.ulysses")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CONFIGS[cfg_key]
+    dim, heads, layers, text_len = cfg["dim"], cfg["heads"], cfg["layers"], cfg["text_len"]
+    f, h, w = cfg["grid"]
+    L = f * h * w
+    if heads % world != 0 or L % world != 0:
+        raise SystemExit(f"{heads} heads / {L} tokens cannot be sharded over {world} ranks")
+    s = L // world
+    peaks = load_peaks()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bf = torch.bfloat16
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident layer inputs (rotating sets, each far larger than the 126 MB L2)
+    n_sets = 4
+    sets = []
+    for _ in range(n_sets):
+        sets.append(dict(
+            q=torch.randn(1, s, dim, device=dev, generator=g).to(bf),
+            k=torch.randn(1, s, dim, device=dev, generator=g).to(bf),
+            v=torch.randn(1, s, heads, 128, device=dev, generator=g).to(bf),
+            qc=torch.randn(1, s, dim, device=dev, generator=g).to(bf),
+            kc=torch.randn(1, text_len, dim, device=dev, generator=g).to(bf),
+            vc=torch.randn(1, text_len, heads, 128, device=dev, generator=g).to(bf)))
+    wn = torch.ones(dim, device=dev)
+    d = 128
+    table = torch.cat([mdl.rope_params(1024, d - 4 * (d // 6)), mdl.rope_params(1024, 2 * (d // 6)),
+                       mdl.rope_params(1024, 2 * (d // 6))], dim=1)
+    cs = mdl._cos_sin_table(table, dev)
+    grid = [(f, h, w)]
+    seq_lens = torch.tensor([L])
+    fmha_events, prol_events = [], []
+
+    def kernel_step(record):
+        """P + S + X of every layer through the C ABI; with world > 1 the Ulysses exchange around S."""
+        for layer in range(layers):
+            t = sets[layer % n_sets]
+            if world == 1:
+                if record:
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    ev[0].record()
+                q, k = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid)
+                if record:
+                    ev[1].record()
+                _ext.fmha_fwd(q, k, t["v"])
+                if record:
+                    ev[2].record()
+                    prol_events.append((ev[0], ev[1]))
+                    fmha_events.append((ev[1], ev[2]))
+            else:
+                q_send, k_send = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs,
+                                                   grid_sizes=grid, tok_offset=rank * s, groups=world)
+                v_send = _ext.head_scatter(t["v"], world)
+                uly.attend_exchanged(q_send, k_send, v_send, seq_lens)
+            qc, _ = _ext.qk_norm_rope(t["qc"], None, wn, None, 1e-6, heads)
+            _, kc = _ext.qk_norm_rope(None, t["kc"], None, wn, 1e-6, heads)
+            _ext.fmha_fwd(qc, kc, t["vc"])
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn(False)
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _ext.launch_count
+        e0.record()
+        for _ in range(steps):
+            fn(True)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms, (_ext.launch_count - n0), clocks
+
+    fs, fc = flops_per_layer(L, heads, text_len)
+    flop_step = (fs + fc) * layers
+    with torch.no_grad():
+        ms_kernel, launches, clocks = timed(kernel_step, args.steps, args.warmup, sample_clocks=True)
+    value = flop_step / (ms_kernel * 1e-3) * 1e-12
+
+    roofline, roofline_prologue = None, None
+    if world == 1 and fmha_events:
+        durs = [a.elapsed_time(b) for a, b in fmha_events]
+        avg = sum(durs) / len(durs)
+        achieved = fs / (avg * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(cfg_key, {}).get("fmha_dram_bytes_per_launch")
+        roofline = {"kernel": "fmha_fwd_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
+                    "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                    "frac_of_burst_peak": achieved / peaks["tflops_burst"], "peak_source": peaks["source"] +
+                    " sustained bf16 (kernel timed inside a long step)", "traffic": traffic,
+                    "avg_launch_ms": avg, "flop_per_launch": fs,
+                    "kernel_share_of_step": avg * layers / ms_kernel}
+        pavg = sum(a.elapsed_time(b) for a, b in prol_events) / len(prol_events)
+        pbytes = 8.0 * L * dim
+        roofline_prologue = {"kernel": "qk_norm_rope_kernel (q/k RMSNorm + 3-D RoPE)", "bound": "hbm",
+                             "achieved": pbytes / (pavg * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                             "peak_source": peaks["source"] + " copy bandwidth", "avg_launch_ms": pavg,
+                             "bytes_per_launch": pbytes, "traffic": None}
+
+    # ---------------- e2e: public module API from pinned host memory ---------------------------------
+    torch.manual_seed(0)
+    sa = mdl.WanSelfAttention(dim, heads).to(dev).eval()
+    ca = mdl.WanCrossAttention(dim, heads).to(dev).eval()
+    for m in (sa, ca):
+        for lin in (m.q, m.k, m.v, m.o):
+            torch.nn.init.xavier_uniform_(lin.weight)
+            torch.nn.init.zeros_(lin.bias)
+    x_host = torch.randn(1, s, dim).to(bf).pin_memory()
+    ctx_host = torch.randn(1, text_len, dim).to(bf).pin_memory()
+    out_host = torch.empty(1, s, dim, dtype=bf).pin_memory()
+    grid_t = torch.tensor([[f, h, w]])
+    table_dev = table.to(dev)
+
+    def e2e_step(_record):
+        x = x_host.to(dev, non_blocking=True)
+        ctx = ctx_host.to(dev, non_blocking=True)
+        with torch.autocast("cuda", dtype=bf):
+            for _ in range(layers):
+                if world == 1:
+                    y = sa(x, seq_lens, grid_t, table_dev)
+                else:
+                    y = sp.sp_attn_forward(sa, x, seq_lens, grid_t, table_dev)
+                x = y + ca(y, ctx, None)
+        out_host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    with torch.no_grad():
+        ms_e2e, _, _ = timed(e2e_step, e2e_steps, 1)
+    e2e = {"value": flop_step / (ms_e2e * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
+           "steps": e2e_steps,
+           "h2d_bytes_per_step": (x_host.numel() + ctx_host.numel()) * 2 * world,
+           "d2h_bytes_per_step": out_host.numel() * 2 * world,
+           "api": "WanSelfAttention.forward + WanCrossAttention.forward per layer (q/k/v/o linears included), "
+                  "x/context from pinned host memory, result copied back"}
+
+    # ---------------- full denoise step through the WanModel harness (once; N = 1 only) ---------------
+    denoise_ms = None
+    if world == 1 and not args.skip_denoise:
+        del sets
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        with torch.device(dev):
+            model = mdl.WanModel(model_type="t2v", dim=dim, ffn_dim=cfg["ffn"], num_heads=heads, num_layers=layers,
+                                 text_len=text_len, in_dim=16, out_dim=16)
+        model = model.eval()
+        lat = [torch.randn(16, f, h * 2, w * 2, device=dev)]
+        ctx = [torch.randn(text_len, 4096, device=dev)]
+        tt = torch.tensor([500.0], device=dev)
+        with torch.no_grad(), torch.autocast("cuda", dtype=bf):
+            model(lat, tt, ctx, seq_len=L)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                model(lat, tt, ctx, seq_len=L)
+            e1.record()
+            torch.cuda.synchronize()
+        denoise_ms = e0.elapsed_time(e1) / 2
+        del model
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            tf, ms, sample, threads = cpu_reference_rate(cfg, 20.0, 2, 1)
+            cpu = {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample,
+                   "ms_per_sample": ms}
+        line = {
+            "metric": "dit_attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, "
+                       "512-key cross-attention) of all layers", "video_tokens": L, "text_tokens": text_len,
+                       "dim": dim, "heads": heads, "layers": layers,
+                       "sharding": "none" if world == 1 else f"Ulysses heads/{world} over NCCL all-to-all",
+                       "l2_policy": "inputs larger than L2: 4 rotating layer-input sets of "
+                                    f"{3 * s * dim * 2 / 1e6:.0f} MB each"},
+            "attention_flop_per_step": flop_step,
+            "denoise_step_ms": denoise_ms,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prologue": roofline_prologue,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default=None, choices=list(CONFIGS))
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
+    ap.add_argument("--skip-denoise", action="store_true", help="omit the full WanModel denoise-step timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    # 12 heads shard over 2 / 4 GPUs (BASELINE configs[2]); 8 GPUs need the 40-head 14B model (configs[3])
+    cfg_key = args.config or ("14B" if args.gpus == 8 else "1.3B")
+    if args.impl == "reference":
+        run_reference_arm(args, cfg_key)
+    else:
+        run_native_arm(args, cfg_key)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+#!/bin/bash
+# One full GPU pass on 1 B200 (run under gpurun): parity tests, smoke, bench, kernel battery, ncu evidence.
+# Usage: bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu_$TAG.log
+echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_$TAG.log
+echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_$TAG.err | tee gpurun_out/bench_$TAG.json
+tail -5 gpurun_out/bench_$TAG.err
+echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref_$TAG.json
+echo "== kernel battery (prologue + cross)"
+T=univid_b200/csrc/tests/uvb_test
+for c in "prol 1 1950 12 1 0 0" "prol 2 300 12 1 1 0" "prol 1 1000 40 1 0 0" "prol 1 500 24 1 0 0" "prol 1 500 10 1 0 0" \
+         "prol 1 32760 12 1 0 20" "prol 1 75600 40 1 0 10" "prol 1 27280 24 1 0 10" "fmha 1 32760 512 12 -1 0 10" "fmha 1 32760 32760 12 -1 0 5"; do
+  echo "-- $c"; timeout 120 $T $c 2>&1 | tail -3
+done | tee gpurun_out/kernels_$TAG.log
+echo "== ncu launch list of the bench command"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fmha_fwd_kernel|qk_norm_rope_kernel|head_scatter_kernel" -c 900 \
+    --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --skip-cpu --skip-denoise > gpurun_out/ncu_bench_$TAG.log 2>&1
+echo "launch list rows: $(wc -l < gpurun_out/launches_$TAG.csv)"
+echo "== ncu --set full: self-attention kernel, prologue kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_fmha_$TAG \
+    $T fmha 1 32760 32760 12 -1 0 1 > gpurun_out/ncu_fmha_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:qk_norm_rope_kernel -s 1 -c 1 -f -o gpurun_out/prof_prol_$TAG \
+    $T prol 1 32760 12 1 0 1 > gpurun_out/ncu_prol_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_xattn_$TAG \
+    $T fmha 1 32760 512 12 -1 0 1 > gpurun_out/ncu_xattn_$TAG.log 2>&1
+ls -la gpurun_out | tail -20

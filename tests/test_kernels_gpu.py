@@ -1,0 +1,182 @@
+"""Parity of the CUDA kernels (through the C ABI) with the CPU oracle on seeded inputs.  -m gpu.
+
+Tolerance (BASELINE.json north_star): per-element max-abs <= 2e-2 and cosine >= 0.9999 against an
+fp32 evaluation; the prologue is compared at bf16 resolution against the oracle's restatement of
+WanRMSNorm + rope_apply (bit-exact except for isolated 1-ulp flips at rounding boundaries)."""
+import pytest
+import torch
+
+from oracle import wan_attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, MIN_COS = 2e-2, 0.9999
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _check_attn(got, want, max_abs=MAX_ABS):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert err <= max_abs, f"max-abs {err}"
+    assert _cos(got, want) >= MIN_COS, f"cos {_cos(got, want)}"
+
+
+def _bf16_close(got, want, frac_exact=0.98):
+    """bf16 tensors equal up to 2 ulp of the rotated pair magnitude, and exactly equal almost everywhere."""
+    got, want = got.float().cpu(), want.float().cpu()
+    pair = want.unflatten(-1, (-1, 2)).abs().amax(-1, keepdim=True).expand(*want.shape[:-1], want.shape[-1] // 2, 2).flatten(-2)
+    tol = 0.0079 * pair + 1e-3
+    assert ((got - want).abs() <= tol).all(), f"max err {(got - want).abs().max()}"
+    assert (got == want).float().mean().item() >= frac_exact
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from univid_b200 import _ext
+    assert _ext.lib().uvb_version() == 100
+    return _ext
+
+
+def _cos_sin(dev):
+    f = orc.make_freqs(128)
+    return f, torch.stack([f.real, f.imag], dim=-1).float().contiguous().to(dev)
+
+
+@pytest.mark.parametrize("heads,dtype", [(12, torch.bfloat16), (2, torch.float32), (40, torch.bfloat16),
+                                         (24, torch.bfloat16), (3, torch.bfloat16), (16, torch.bfloat16)])
+def test_qk_norm_rope_matches_oracle(ext, heads, dtype):
+    dev = "cuda"
+    g = torch.Generator().manual_seed(heads)
+    dim = heads * 128
+    b, l = 2, 130
+    grid = torch.tensor([[2, 5, 13], [3, 6, 7]])       # 130 and 126 real tokens (4 pad tokens in sample 1)
+    q = torch.randn(b, l, dim, generator=g).to(dtype)
+    k = (0.5 * torch.randn(b, l, dim, generator=g)).to(dtype)
+    wq, wk = 1 + 0.1 * torch.randn(dim, generator=g), 1 + 0.1 * torch.randn(dim, generator=g)
+    freqs, cs = _cos_sin(dev)
+    q_out, k_out = ext.qk_norm_rope(q.to(dev), k.to(dev), wq.to(dev), wk.to(dev), 1e-6, heads, cos_sin=cs,
+                                    grid_sizes=grid)
+    torch.cuda.synchronize()
+    for got, x, w in ((q_out, q, wq), (k_out, k, wk)):
+        want = orc.rope_apply(orc.rms_norm(x, w, 1e-6).view(b, l, heads, 128), grid, freqs).to(torch.bfloat16)
+        _bf16_close(got, want)
+
+
+def test_qk_norm_without_rope_and_without_norm(ext):
+    dev = "cuda"
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 77, 1536, generator=g).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(1536, generator=g)
+    _, k_out = ext.qk_norm_rope(None, x.to(dev), None, w.to(dev), 1e-6, 12)
+    _bf16_close(k_out, orc.rms_norm(x, w, 1e-6).view(1, 77, 12, 128).to(torch.bfloat16))
+    # qk_norm=False: rotation only
+    freqs, cs = _cos_sin(dev)
+    grid = torch.tensor([[1, 7, 11]])
+    q_out, _ = ext.qk_norm_rope(x.to(dev), None, None, None, 1e-6, 12, cos_sin=cs, grid_sizes=grid)
+    _bf16_close(q_out, orc.rope_apply(x.view(1, 77, 12, 128), grid, freqs).to(torch.bfloat16))
+
+
+def test_qk_norm_rope_sequence_parallel_offset_and_send_layout(ext):
+    """tok_offset reproduces the rank slice of the SP rope (sequence_parallel.py:46-55) and groups=p writes
+    the Ulysses send layout [p, B, s, N/p, 128] (util.py:27 chunk on the head dimension)."""
+    dev = "cuda"
+    g = torch.Generator().manual_seed(9)
+    heads, dim, world, s = 4, 512, 2, 32
+    grid = torch.tensor([[3, 4, 5]])                    # 60 real tokens, padded to 64
+    x = torch.randn(1, world * s, dim, generator=g).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(dim, generator=g)
+    freqs, cs = _cos_sin(dev)
+    for r in range(world):
+        xr = x[:, r * s:(r + 1) * s].contiguous()
+        q_send, _ = ext.qk_norm_rope(xr.to(dev), None, w.to(dev), None, 1e-6, heads, cos_sin=cs, grid_sizes=grid,
+                                     tok_offset=r * s, groups=world)
+        assert q_send.shape == (world, 1, s, heads // world, 128)
+        want = orc.sp_rope_apply(orc.rms_norm(xr, w, 1e-6).view(1, s, heads, 128), grid, freqs, r, world)
+        want = torch.stack(want.to(torch.bfloat16).chunk(world, dim=2))
+        _bf16_close(q_send, want)
+
+
+def test_head_scatter(ext):
+    v = torch.randn(2, 50, 6, 128, dtype=torch.bfloat16, device="cuda")
+    out = ext.head_scatter(v, 3)
+    assert torch.equal(out, torch.stack(v.chunk(3, dim=2)))
+
+
+@pytest.mark.parametrize("b,lq,lk,n", [(1, 128, 128, 1), (1, 256, 384, 2), (2, 1950, 1950, 3), (1, 300, 77, 2),
+                                       (1, 1, 1, 1), (3, 129, 513, 1), (1, 1950, 512, 12)])
+def test_fmha_matches_oracle(ext, b, lq, lk, n):
+    g = torch.Generator().manual_seed(lq * 7 + lk)
+    q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda())
+    _check_attn(got, orc.attention_varlen(q, k, v, compute_dtype=torch.float32))
+
+
+def test_fmha_peaked_logits_exercise_the_lazy_rescale(ext):
+    """Row maxima that grow by far more than 2^8 from one key tile to the next force the in-place
+    rescale of the TMEM accumulator."""
+    g = torch.Generator().manual_seed(1)
+    lq, lk = 256, 1024
+    q = torch.randn(1, lq, 2, 128, generator=g)
+    k = torch.randn(1, lk, 2, 128, generator=g)
+    k = k * torch.linspace(0.2, 6.0, lk).view(1, lk, 1, 1)      # logits grow along the key axis
+    v = torch.randn(1, lk, 2, 128, generator=g)
+    q, k, v = (u.to(torch.bfloat16) for u in (q, k, v))
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda())
+    _check_attn(got, orc.attention_varlen(q, k, v, compute_dtype=torch.float32), max_abs=4e-2)
+
+
+@pytest.mark.parametrize("lens", [[1000, 1950], [1, 128], [129, 0], [1950, 1950]])
+def test_fmha_key_lengths(ext, lens):
+    g = torch.Generator().manual_seed(sum(lens))
+    q, k, v = (torch.randn(2, 1950 if i else 300, 2, 128, generator=g).to(torch.bfloat16) for i in range(3))
+    kl = torch.tensor(lens, dtype=torch.int32)
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=kl.cuda())
+    _check_attn(got, orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32))
+
+
+def test_fmha_strided_views_and_scale(ext):
+    """q/k/v as slices of one fused [B, L, 3, N, 128] projection and of a wider head tensor; custom scale."""
+    g = torch.Generator().manual_seed(2)
+    qkv = torch.randn(1, 200, 3, 4, 128, generator=g).to(torch.bfloat16).cuda()
+    q, k, v = qkv[:, :, 0, 1:3], qkv[:, :, 1, 1:3], qkv[:, :, 2, 1:3]
+    out = torch.zeros(1, 200, 4, 128, dtype=torch.bfloat16, device="cuda")
+    ext.fmha_fwd(q, k, v, softmax_scale=0.05, out=out[:, :, 2:4])
+    want = orc.attention_varlen(q.cpu(), k.cpu(), v.cpu(), softmax_scale=0.05, compute_dtype=torch.float32)
+    _check_attn(out[:, :, 2:4], want)
+    assert torch.count_nonzero(out[:, :, 0:2]) == 0
+
+
+def test_xattn_key_modifiers(ext):
+    g = torch.Generator().manual_seed(3)
+    lq, lk, n = 500, 512, 3
+    q, k, v = (torch.randn(1, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+    temp = torch.ones(lk)
+    temp[:128] = 1.3
+    w = torch.ones(lk)
+    w[:128] = 1.25
+    bias = 0.1 * torch.randn(n * 128, generator=g)
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), key_logit_scale=temp.cuda(), key_pv_weight=w.cuda(),
+                       out_bias=bias.cuda())
+    want = orc.attention_varlen(q, k, v, compute_dtype=torch.float32, key_logit_scale=temp, key_pv_weight=w,
+                                out_bias=bias)
+    _check_attn(got, want)
+    # each modifier alone; Lk not a multiple of the key tile
+    k2, v2 = k[:, :300], v[:, :300]
+    got = ext.fmha_fwd(q.cuda(), k2.cuda(), v2.cuda(), key_pv_weight=w[:300].cuda())
+    _check_attn(got, orc.attention_varlen(q, k2, v2, compute_dtype=torch.float32, key_pv_weight=w[:300]))
+    got = ext.fmha_fwd(q.cuda(), k2.cuda(), v2.cuda(), key_logit_scale=temp[:300].cuda())
+    _check_attn(got, orc.attention_varlen(q, k2, v2, compute_dtype=torch.float32, key_logit_scale=temp[:300]))
+
+
+def test_unsupported_shapes_raise(ext):
+    q = torch.zeros(1, 8, 2, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ext.fmha_fwd(q, q, q)
+    q = torch.zeros(1, 8, 2, 128, dtype=torch.float16, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ext.fmha_fwd(q, q, q)
