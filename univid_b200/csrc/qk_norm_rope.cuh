@@ -56,9 +56,13 @@ struct RowVec<__nv_bfloat16> {
       f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
-  // `.type_as(x)`: round the normalised value to the input dtype
-  static __device__ __forceinline__ float round_in(float x) {
-    return __bfloat162float(__float2bfloat16_rn(x));
+  // `.type_as(x)`: round the normalised values to the input dtype.  Done two at a time through the
+  // packed F2FP convert + shifts: the scalar F2F.BF16.F32 runs on the quarter-rate XU pipe and made
+  // the kernel issue-bound (profiles/r01: 34 % XU, 46 % DRAM).
+  static __device__ __forceinline__ void round_in2(float& a, float& b) {
+    const uint32_t pk = pack_bf16x2(a, b);
+    a = __uint_as_float(pk << 16);
+    b = __uint_as_float(pk & 0xffff0000u);
   }
 };
 
@@ -73,7 +77,7 @@ struct RowVec<float> {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
     f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
-  static __device__ __forceinline__ float round_in(float x) { return x; }
+  static __device__ __forceinline__ void round_in2(float&, float&) {}
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -84,11 +88,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Normalise + rotate one row and store it.  The row stays PACKED in registers (VPL x 16 bytes per
 // lane for bf16) and is unpacked twice -- once for the sum of squares, once for the output -- which
-// keeps the register footprint small enough for >= 32 resident warps per SM at dim 5120.
+// keeps the register footprint small enough for 24-32 resident warps per SM.
 //
 // WPR warps cooperate on one row (lane index `lane` in [0, 32*WPR)); their partial sums of squares
-// meet in shared memory behind a named barrier private to the row.
-template <typename InT, int VPL, int WPR>
+// meet in shared memory behind a named barrier private to the row.  kPre selects the affine
+// pre-map x <- rscale * x + pre_bias (text-weighted context rows).
+template <typename InT, int VPL, int WPR, bool kPre>
 __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const float* __restrict__ w,
                                               __nv_bfloat16* __restrict__ out_row, int hpg,
                                               long long out_sg, int dim, float eps, bool rotate,
@@ -102,24 +107,31 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
 
   auto fetch = [&](int i, float* x) {
     v[i].unpack(x);
-    if (pre_bias != nullptr) {
+    if constexpr (kPre) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + kStride * i) * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(pre_bias + (lane + kStride * i) * 8) + 1);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = RowVec<InT>::round_in(fmaf(rscale, x[e], bb[e]));
+      for (int e = 0; e < 8; e += 2) {
+        x[e] = fmaf(rscale, x[e], bb[e]);
+        x[e + 1] = fmaf(rscale, x[e + 1], bb[e + 1]);
+        RowVec<InT>::round_in2(x[e], x[e + 1]);
+      }
     }
   };
 
-  float ss = 0.f;
+  float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float x[8];
     fetch(i, x);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+    for (int e = 0; e < 8; e += 2) {
+      ss0 = fmaf(x[e], x[e], ss0);
+      ss1 = fmaf(x[e + 1], x[e + 1], ss1);
+    }
   }
-  ss = warp_sum(ss);
+  float ss = warp_sum(ss0 + ss1);
   if constexpr (WPR > 1) {
     if ((lane & 31) == 0) red[lane >> 5] = ss;
     named_bar_sync(bar_id, kStride);
@@ -130,22 +142,25 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
   // w == nullptr: qk_norm disabled (nn.Identity, model.py:123-124) -> rotation only
   const bool normed = w != nullptr;
   const float rinv = normed ? rsqrtf(ss / static_cast<float>(dim) + eps) : 1.0f;
+  const bool flat = hpg * 128 == dim;   // one head group: output rows are dense [N, 128]
 
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vec = lane + kStride * i;
-    float x[8];
-    fetch(i, x);
     float y[8];
+    fetch(i, y);
     if (normed) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vec * 8));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vec * 8) + 1);
       const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = RowVec<InT>::round_in(x[e] * rinv) * ww[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = x[e];
+      for (int e = 0; e < 8; e += 2) {
+        y[e] *= rinv;
+        y[e + 1] *= rinv;
+        RowVec<InT>::round_in2(y[e], y[e + 1]);
+        y[e] *= ww[e];
+        y[e + 1] *= ww[e + 1];
+      }
     }
     uint32_t o[4];
 #pragma unroll
@@ -160,9 +175,14 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
       }
       o[pr] = pack_bf16x2(a, b);
     }
-    const int n = vec >> 4;            // head index
-    const int d0 = (vec & 15) * 8;     // offset inside the head
-    __nv_bfloat16* dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+    __nv_bfloat16* dst;
+    if (flat) {
+      dst = out_row + vec * 8;                 // [.., N, 128] rows are dense
+    } else {
+      const int n = vec >> 4;                  // head index
+      const int d0 = (vec & 15) * 8;           // offset inside the head
+      dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+    }
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o[0]),
                  "r"(o[1]), "r"(o[2]), "r"(o[3])
                  : "memory");
@@ -186,9 +206,16 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
     v.load(in + vec * 8);
     float x[8];
     v.unpack(x);
+    if (pre_bias != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        x[e] = fmaf(rscale, x[e], pre_bias[vec * 8 + e]);
+        x[e + 1] = fmaf(rscale, x[e + 1], pre_bias[vec * 8 + e + 1]);
+        RowVec<InT>::round_in2(x[e], x[e + 1]);
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (pre_bias != nullptr) x[e] = RowVec<InT>::round_in(fmaf(rscale, x[e], pre_bias[vec * 8 + e]));
       ss = fmaf(x[e], x[e], ss);
     }
   }
@@ -205,12 +232,16 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
     for (int pr = 0; pr < 4; ++pr) {
       float a = x[2 * pr], b = x[2 * pr + 1];
       if (pre_bias != nullptr) {
-        a = RowVec<InT>::round_in(fmaf(rscale, a, pre_bias[vec * 8 + 2 * pr]));
-        b = RowVec<InT>::round_in(fmaf(rscale, b, pre_bias[vec * 8 + 2 * pr + 1]));
+        a = fmaf(rscale, a, pre_bias[vec * 8 + 2 * pr]);
+        b = fmaf(rscale, b, pre_bias[vec * 8 + 2 * pr + 1]);
+        RowVec<InT>::round_in2(a, b);
       }
       if (normed) {
-        a = RowVec<InT>::round_in(a * rinv) * w[vec * 8 + 2 * pr];
-        b = RowVec<InT>::round_in(b * rinv) * w[vec * 8 + 2 * pr + 1];
+        a *= rinv;
+        b *= rinv;
+        RowVec<InT>::round_in2(a, b);
+        a *= w[vec * 8 + 2 * pr];
+        b *= w[vec * 8 + 2 * pr + 1];
       }
       if (rotate) {
         const float c = cs[2 * pr], s = cs[2 * pr + 1];
@@ -282,8 +313,13 @@ qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
   const float* pre_bias = is_k ? p.pre_bias : nullptr;
   const float rscale = (is_k && p.row_scale != nullptr) ? p.row_scale[l] : 1.0f;
   if constexpr (VPL > 0) {
-    norm_rope_row<InT, VPL, WPR>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
-                                 rscale, pre_bias, lane, red + group * WPR, 1 + group);
+    if (pre_bias != nullptr) {
+      norm_rope_row<InT, VPL, WPR, true>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
+                                         rscale, pre_bias, lane, red + group * WPR, 1 + group);
+    } else {
+      norm_rope_row<InT, VPL, WPR, false>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
+                                          rscale, nullptr, lane, red + group * WPR, 1 + group);
+    }
   } else {
     norm_rope_row_generic<InT>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs, rscale,
                                pre_bias, lane);
