@@ -2,6 +2,7 @@
 // TMA tensor-map construction and kernel launches.  No torch types, no device allocation, no sync.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/univid_b200.h"
@@ -119,7 +120,13 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
 
-  auto kern = uvb::fmha_fwd_kernel<kFmhaStages, kKeyMod>;
+  // UVB_FMHA_STEP=64|128 selects the sub-step variant (tuning hook; default below)
+  static const int step_n = [] {
+    const char* e = getenv("UVB_FMHA_STEP");
+    return (e != nullptr && atoi(e) == 64) ? 64 : 128;
+  }();
+  auto kern = step_n == 64 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, kKeyMod>
+                           : uvb::fmha_fwd_kernel<kFmhaStages, 128, kKeyMod>;
   constexpr int smem = uvb::FmhaSmem<kFmhaStages>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const dim3 grid((Lq + uvb::kQTiles * uvb::kBlockM - 1) / (uvb::kQTiles * uvb::kBlockM), N, B);

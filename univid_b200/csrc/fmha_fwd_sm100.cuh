@@ -9,25 +9,29 @@
 //   warp  8     tcgen05.mma issuer (one elected thread) + TMEM allocator     setmaxnreg.dec
 //   warp  9     TMA producer (one elected thread)                            setmaxnreg.dec
 //   warps 10-11 idle (they only exist so the third warpgroup can give its registers away)
-// TMEM (512 columns x 128 lanes):  S0 | S1 | O0 | O1, 128 fp32 columns each.  P (bf16) aliases the
-// first 64 columns of its S tile and is consumed as the A operand of the PV MMA straight from TMEM.
+// TMEM (512 columns x 128 lanes):  S0a S0b | S1a S1b | O0 | O1.  The key axis advances in 64-key
+// sub-steps and every query tile owns TWO 64-column S buffers, so the MMA thread issues
+// S_t(s+2) = Q_t K(s+2)^T right after O_t += P_t(s) V(s): while the softmax group works on step s the
+// scores of step s+1 are already (being) computed, and the softmax<->MMA hand-off is a producer/consumer
+// pipeline instead of a serial dependency chain (round-1 ncu: with one S buffer per tile the softmax warps
+// spent half their time waiting for S and the tensor pipe was 53 % busy).  P (bf16) aliases the first 32
+// columns of its S buffer and is consumed as the A operand of the PV MMA straight from TMEM.
 // K/V tiles (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem and its
 // buffer is reused to stage O for the TMA store.
 //
-// Per KV tile j and query tile t the dependency chain is
-//   S_t = Q_t K_j^T  (SS MMA)  -> s_full[t] -> softmax (row max, lazy rescale of O_t, exp2, row sum,
-//   P_t -> TMEM) -> p_full[t] -> O_t += P_t V_j (TS MMA) ; S_t = Q_t K_{j+1}^T ...
-// and the two query tiles ping-pong so the tensor pipe works on one while the other is in softmax.
-// tcgen05 MMAs issued by one thread execute in order, so S_t(j+1) overwriting the P_t(j) columns is
-// safe, and s_full[t] (a tcgen05.commit) also implies PV_t(j-1) has completed, which is what allows
-// the softmax warps to rescale O_t in place without a dedicated correction group.
+// Ordering facts the protocol relies on: tcgen05 MMAs issued by one thread execute in order, so
+// S_t(s+2) overwriting the buffer that held P_t(s) is safe once PV_t(s) has been issued before it; the
+// softmax warps rescale O_t in place (lazily, only when a row max grows by more than 2^8) after waiting
+// for pv_done[t] of the previous step, and PV_t(s) is not issued before they arrive on p_full[t].
 #pragma once
 #include "ptx.cuh"
 
 namespace uvb {
 
 constexpr int kBlockM = 128;          // query rows per tile (UMMA M)
-constexpr int kBlockN = 128;          // keys per KV tile  (UMMA N of QK^T, K of PV)
+constexpr int kBlockN = 128;          // keys per K/V smem tile (TMA granularity)
+// kStepN (template): keys per softmax/MMA sub-step (UMMA N of QK^T, K of PV): 128 -> one S buffer per
+// query tile, 64 -> two S buffers per tile (the MMA thread runs two steps ahead of the softmax)
 constexpr int kHeadDim = 128;
 constexpr int kQTiles = 2;            // query tiles per CTA
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;   // 32 KiB, one [128 x 128] bf16 tile
@@ -42,8 +46,8 @@ struct FmhaSmem {
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQTiles * kTileBytes;
   static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
-  // barriers: q_full[2] kv_full[S] kv_empty[S] s_full[2] p_full[2] o_full[2] + tmem ptr
-  static constexpr int kNumBars = 2 + 2 * kStages + 6;
+  // barriers: q_full[2] kv_full[S] kv_empty[S] s_full[2][2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
+  static constexpr int kNumBars = 2 + 2 * kStages + 12;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for 1024 B alignment
 };
@@ -62,9 +66,11 @@ struct FmhaParams {
   float scale_log2;               // softmax_scale * log2(e)
 };
 
-template <int kStages, bool kKeyMod>
+template <int kStages, int kStepN, bool kKeyMod>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
+  static_assert(kStepN == 64 || kStepN == 128, "sub-step must be 64 or 128 keys");
+  constexpr int kNB = kBlockN / kStepN;   // S buffers per query tile == sub-steps per K/V tile
   using SM = FmhaSmem<kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -75,9 +81,10 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   uint64_t* q_full = bars;                       // [2]
   uint64_t* kv_full = bars + 2;                  // [kStages]
   uint64_t* kv_empty = kv_full + kStages;        // [kStages]
-  uint64_t* s_full = kv_empty + kStages;         // [2]
-  uint64_t* p_full = s_full + 2;                 // [2]
-  uint64_t* o_full = p_full + 2;                 // [2]
+  uint64_t* s_full = kv_empty + kStages;         // [tile][buffer]
+  uint64_t* p_full = s_full + 4;                 // [tile][buffer]
+  uint64_t* pv_done = p_full + 4;                // [tile]
+  uint64_t* o_full = pv_done + 2;                // [tile]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -88,7 +95,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
   int k_len = p.Lk;
   if (p.k_lens != nullptr) k_len = min(max(p.k_lens[batch], 0), p.Lk);
-  const int n_kv = (k_len + kBlockN - 1) / kBlockN;
+  const int n_kv = (k_len + kBlockN - 1) / kBlockN;     // K/V tiles to load
+  const int n_steps = (k_len + kStepN - 1) / kStepN;    // sub-steps
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full[0], 1);
@@ -98,8 +106,11 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       mbar_init(&kv_empty[i], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], kBlockM);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[2 * t + b], 1);
+        mbar_init(&p_full[2 * t + b], 4);   // one arrive per softmax warp
+      }
+      mbar_init(&pv_done[t], 1);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -117,105 +128,137 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // warp-uniform copy (a plain smem load is not provably uniform and would force ptxas to wrap every
+  // tcgen05 instruction in an R2UR.BROADCAST waterfall loop)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if (n_kv > 0 && warp == 9) {
       // ===================================== TMA producer =====================================
-      if (lane == 0) {
-        for (int t = 0; t < kQTiles; ++t) {
+      // the whole warp runs the loop (converged, uniform operands); one elected lane issues
+      for (int t = 0; t < kQTiles; ++t) {
+        uint8_t* dst = smem_q + t * kTileBytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&q_full[t], kTileBytes);
-          uint8_t* dst = smem_q + t * kTileBytes;
-          tma_load_4d_hint(dst, &p.tm_q, &q_full[t], 0, q_row0 + t * kBlockM, head, batch,
+          tma_load_4d_hint(dst, &p.tm_q, &q_full[t], 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+          tma_load_4d_hint(dst + kHalfTile, &p.tm_q, &q_full[t], 64, q_row0 + t * kBlockM, head, batch,
                            kEvictFirst);
-          tma_load_4d_hint(dst + kHalfTile, &p.tm_q, &q_full[t], 64, q_row0 + t * kBlockM, head,
-                           batch, kEvictFirst);
         }
-        // ring order matches consumption order: K0, V0, K1, V1, ...
-        const int total = 2 * n_kv;
-        for (int i = 0; i < total; ++i) {
-          const int stage = i % kStages;
-          const uint32_t phase = (i / kStages) & 1;
-          mbar_wait(&kv_empty[stage], phase ^ 1);
+        __syncwarp();
+      }
+      // ring order matches consumption order: K0, V0, K1, V1, ...
+      const int total = 2 * n_kv;
+      for (int i = 0; i < total; ++i) {
+        const int stage = i % kStages;
+        const uint32_t phase = (i / kStages) & 1;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* dst = smem_kv + stage * kTileBytes;
+        const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
+        const int key0 = (i >> 1) * kBlockN;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[stage], kTileBytes);
-          uint8_t* dst = smem_kv + stage * kTileBytes;
-          const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
-          const int key0 = (i >> 1) * kBlockN;
           tma_load_4d_hint(dst, tm, &kv_full[stage], 0, key0, head, batch, kEvictLast);
           tma_load_4d_hint(dst + kHalfTile, tm, &kv_full[stage], 64, key0, head, batch, kEvictLast);
         }
+        __syncwarp();
       }
     } else if (n_kv > 0 && warp == 8) {
       // ===================================== MMA issuer =======================================
-      if (lane == 0) {
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
-        const uint32_t q_addr = smem_u32(smem_q);
-        const uint32_t kv_addr = smem_u32(smem_kv);
+      // The whole warp runs the control flow converged so every operand is warp-uniform; one elected
+      // lane (always the same one) issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are
+      // built once; per instruction only a 64-bit add of a compile-time offset remains.  (Round-1 ncu:
+      // with the loop inside `if (lane == 0)` ptxas emitted an ELECT/R2UR.BROADCAST waterfall around each
+      // UTCHMMA and descriptor math on the uniform datapath -- ~110 cycles per MMA, the real bottleneck.)
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kStepN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(smem_q), 16, 1024);            // K-major A
+      const uint64_t k_desc = umma_desc_sw128(smem_u32(smem_kv), 16, 1024);           // K-major B
+      const uint64_t v_desc = umma_desc_sw128(smem_u32(smem_kv), kHalfTile, 1024);    // MN-major B
+      constexpr uint64_t kTile16 = kTileBytes >> 4;           // descriptor address units are 16 B
+      constexpr uint64_t kStep16 = (kStepN * 128) >> 4;       // kStepN key rows of one 128 B panel
 
-        // S_t = Q_t K^T : A, B K-major; 8 K-steps of 16; panel = kk/4, 32 B per step in the atom
-        auto issue_qk = [&](int t, uint32_t k_stage_addr) {
-          const uint32_t qa = q_addr + t * kTileBytes;
-  #pragma unroll
+      auto wait_full = [&](int ring) {
+        mbar_wait(&kv_full[ring % kStages], (ring / kStages) & 1);
+        tc_fence_after();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) tc_commit(bar);
+        __syncwarp();
+      };
+      // S_t[buf] = Q_t K(step)^T : A, B K-major, N = kStepN keys; 8 K-steps of 16 dims: panel = kk/4,
+      // 32 B per K-step inside the 128 B swizzle atom
+      auto issue_qk = [&](int t, int step, int buf) {
+        const uint64_t qa = q_desc + t * kTile16;
+        const uint64_t ka = k_desc + ((2 * (step / kNB)) % kStages) * kTile16 + (step % kNB) * kStep16;
+        const uint32_t d = tmem_base + t * 128 + buf * kStepN;
+        if (elect_one()) {
+#pragma unroll
           for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-            const uint32_t off = (kk >> 2) * kHalfTile + (kk & 3) * 32;
-            umma_ss(tmem_base + t * kBlockN, umma_desc_sw128(qa + off, 16, 1024),
-                    umma_desc_sw128(k_stage_addr + off, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+            const uint64_t off = ((kk >> 2) * kHalfTile + (kk & 3) * 32) >> 4;
+            umma_ss(d, qa + off, ka + off, idesc_qk, kk > 0 ? 1u : 0u);
           }
-        };
-        // O_t (+)= P_t V : A = P from TMEM (8 columns per 16 keys), B = V, MN-major:
-        // 16 keys = 2 KiB per step, the two 64-dim panels are kHalfTile apart (LBO), 8-key groups 1 KiB (SBO)
-        auto issue_pv = [&](int t, uint32_t v_stage_addr, bool accumulate) {
-  #pragma unroll
-          for (int kk = 0; kk < kBlockN / 16; ++kk) {
-            umma_ts(tmem_base + 2 * kBlockN + t * kHeadDim, tmem_base + t * kBlockN + kk * 8,
-                    umma_desc_sw128(v_stage_addr + kk * 2048, kHalfTile, 1024), idesc_pv,
-                    (accumulate || kk > 0) ? 1u : 0u);
-          }
-        };
-
-        int it = 0;  // ring index
-        mbar_wait(&q_full[0], 0);
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        issue_qk(0, kv_addr);
-        tc_commit(&s_full[0]);
-        mbar_wait(&q_full[1], 0);
-        tc_fence_after();
-        issue_qk(1, kv_addr);
-        tc_commit(&s_full[1]);
-        tc_commit(&kv_empty[0]);
-        it = 1;
-        for (int j = 0; j < n_kv; ++j) {
-          const bool has_next = (j + 1) < n_kv;
-          const int sv = it % kStages;
-          const uint32_t pv_phase = (it / kStages) & 1;
-          const int sk = (it + 1) % kStages;
-          const uint32_t pk_phase = ((it + 1) / kStages) & 1;
-          const uint32_t v_addr = kv_addr + sv * kTileBytes;
-          const uint32_t k_addr = kv_addr + sk * kTileBytes;
-          mbar_wait(&kv_full[sv], pv_phase);
-  #pragma unroll
-          for (int t = 0; t < kQTiles; ++t) {
-            mbar_wait(&p_full[t], j & 1);
-            tc_fence_after();
-            issue_pv(t, v_addr, j > 0);
-            if (has_next) {
-              if (t == 0) {
-                mbar_wait(&kv_full[sk], pk_phase);
-                tc_fence_after();
-              }
-              issue_qk(t, k_addr);
-              tc_commit(&s_full[t]);
-            } else {
-              tc_commit(&o_full[t]);
-            }
-          }
-          tc_commit(&kv_empty[sv]);
-          if (has_next) tc_commit(&kv_empty[sk]);
-          it += 2;
         }
+        __syncwarp();
+      };
+      // O_t (+)= P_t[buf] V(step) : A = P from TMEM (8 columns per 16 keys), B = V rows of the step,
+      // MN-major: 16 keys = 2 KiB per K-step, the two 64-dim panels are kHalfTile apart (LBO), 8-key
+      // groups 1 KiB apart (SBO)
+      auto issue_pv = [&](int t, int step, int buf) {
+        const uint64_t va = v_desc + ((2 * (step / kNB) + 1) % kStages) * kTile16 + (step % kNB) * kStep16;
+        const uint32_t d = tmem_base + 256 + t * kHeadDim;
+        const uint32_t a = tmem_base + t * 128 + buf * kStepN;
+        const uint32_t acc0 = step > 0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kStepN / 16; ++kk) {
+            umma_ts(d, a + kk * 8, va + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+          }
+        }
+        __syncwarp();
+      };
+      // a K/V tile is last read by its last sub-step (or by the very last step)
+      auto last_use = [&](int step) { return (step % kNB) == kNB - 1 || step == n_steps - 1; };
+
+      // prologue: scores of the first kNB steps into the S buffers of each tile
+      mbar_wait(&q_full[0], 0);
+      wait_full(0);
+      const int pre = n_steps < kNB ? n_steps : kNB;
+      for (int t = 0; t < kQTiles; ++t) {
+        if (t == 1) {
+          mbar_wait(&q_full[1], 0);
+          tc_fence_after();
+        }
+        for (int s0 = 0; s0 < pre; ++s0) {
+          issue_qk(t, s0, s0);
+          commit(&s_full[2 * t + s0]);
+        }
+      }
+      commit(&kv_empty[0]);   // K tile 0 is fully consumed by the prologue
+
+      for (int step = 0; step < n_steps; ++step) {
+        const int buf = step % kNB;
+        const uint32_t par = (step / kNB) & 1;
+        const int nxt = step + kNB;
+        const int v_ring = 2 * (step / kNB) + 1;
+        const int k_ring = 2 * (nxt / kNB);
+        if (buf == 0) wait_full(v_ring);                            // V tile of this step group
+#pragma unroll
+        for (int t = 0; t < kQTiles; ++t) {
+          mbar_wait(&p_full[2 * t + buf], par);
+          tc_fence_after();
+          issue_pv(t, step, buf);
+          commit(&pv_done[t]);
+          if (nxt < n_steps) {
+            if (t == 0 && (nxt % kNB) == 0) wait_full(k_ring);      // next K tile
+            issue_qk(t, nxt, buf);
+            commit(&s_full[2 * t + buf]);
+          } else if (step == n_steps - 1) {
+            commit(&o_full[t]);
+          }
+        }
+        if (last_use(step)) commit(&kv_empty[v_ring % kStages]);
+        if (nxt < n_steps && last_use(nxt)) commit(&kv_empty[k_ring % kStages]);
       }
     }
   } else {
@@ -244,28 +287,31 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       const int wq = warp & 3;
       const int row = wq * 32 + lane;
       const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-      const uint32_t tS = tmem_base + lane_addr + t * kBlockN;
-      const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim;
+      const uint32_t tS = tmem_base + lane_addr + t * 128;
+      const uint32_t tO = tmem_base + lane_addr + 256 + t * kHeadDim;
       const float scale_log2 = p.scale_log2;
       float m = -INFINITY;  // running row max in raw-logit units
       float l = 0.f;        // running row sum of exp2((s - m) * scale_log2)
 
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
+      for (int step = 0; step < n_steps; ++step) {
+        const int buf = step % kNB;
+        mbar_wait(&s_full[2 * t + buf], (step / kNB) & 1);
         tc_fence_after();
-        uint32_t sr[kBlockN];
-        tmem_ld_x32(tS + 0, sr + 0);
-        tmem_ld_x32(tS + 32, sr + 32);
-        tmem_ld_x32(tS + 64, sr + 64);
-        tmem_ld_x32(tS + 96, sr + 96);
+        uint32_t sr[kStepN];
+        tmem_ld_x32(tS + buf * kStepN, sr);
+        tmem_ld_x32(tS + buf * kStepN + 32, sr + 32);
+        if constexpr (kStepN == 128) {
+          tmem_ld_x32(tS + buf * kStepN + 64, sr + 64);
+          tmem_ld_x32(tS + buf * kStepN + 96, sr + 96);
+        }
         tmem_wait_ld();
 
         if constexpr (kKeyMod) {
           if (p.key_logit_scale != nullptr) {
-            const float4* ks = reinterpret_cast<const float4*>(p.key_logit_scale + j * kBlockN);
-  #pragma unroll
-            for (int c = 0; c < kBlockN / 4; ++c) {
-              // tail reads past Lk are masked below; the host pads the array to a tile multiple
+            const float4* ks = reinterpret_cast<const float4*>(p.key_logit_scale + step * kStepN);
+#pragma unroll
+            for (int c = 0; c < kStepN / 4; ++c) {
+              // entries past Lk are masked below; the host pads the array to a multiple of 128
               const float4 w = __ldg(ks + c);
               sr[4 * c + 0] = __float_as_uint(__uint_as_float(sr[4 * c + 0]) * w.x);
               sr[4 * c + 1] = __float_as_uint(__uint_as_float(sr[4 * c + 1]) * w.y);
@@ -274,18 +320,18 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             }
           }
         }
-        const int valid = k_len - j * kBlockN;
-        if (valid < kBlockN) {
-  #pragma unroll
-          for (int c = 0; c < kBlockN; ++c) {
+        const int valid = k_len - step * kStepN;
+        if (valid < kStepN) {
+#pragma unroll
+          for (int c = 0; c < kStepN; ++c) {
             if (c >= valid) sr[c] = 0xff800000u;  // -inf
           }
         }
 
         float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
         float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
-  #pragma unroll
-        for (int c = 4; c < kBlockN; c += 4) {
+#pragma unroll
+        for (int c = 4; c < kStepN; c += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
           mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
@@ -293,23 +339,25 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
-        if (j == 0) {
+        if (step == 0) {
           m = tile_max;
         } else {
           const bool need = (tile_max - m) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // s_full[t] of this iteration implies PV_t(j-1) is complete and PV_t(j) is not issued
-            // until we arrive on p_full[t]: O_t is ours to rescale.
+            // O_t may still be accumulating PV_t(step-1): wait for it.  PV_t(step) cannot be issued
+            // before we arrive on p_full below, so pv_done[t] is at most one phase ahead of us.
+            mbar_wait(&pv_done[t], (step - 1) & 1);
+            tc_fence_after();
             const float m_new = fmaxf(m, tile_max);
             const float f = ex2_approx((m - m_new) * scale_log2);
             l *= f;
             m = m_new;
-  #pragma unroll
+#pragma unroll
             for (int c = 0; c < kHeadDim / 32; ++c) {
               uint32_t orr[32];
               tmem_ld_x32(tO + c * 32, orr);
               tmem_wait_ld();
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
               tmem_st_x32(tO + c * 32, orr);
             }
@@ -319,13 +367,13 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
         const float neg_ms = -m * scale_log2;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-        uint32_t pk[kBlockN / 2];
+        uint32_t pk[kStepN / 2];
         const float* pvw = nullptr;
         if constexpr (kKeyMod) {
-          if (p.key_pv_weight != nullptr) pvw = p.key_pv_weight + j * kBlockN;
+          if (p.key_pv_weight != nullptr) pvw = p.key_pv_weight + step * kStepN;
         }
-  #pragma unroll
-        for (int c = 0; c < kBlockN; c += 4) {
+#pragma unroll
+        for (int c = 0; c < kStepN; c += 4) {
           float e0 = ex2_approx(fmaf(__uint_as_float(sr[c + 0]), scale_log2, neg_ms));
           float e1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_ms));
           float e2 = ex2_approx(fmaf(__uint_as_float(sr[c + 2]), scale_log2, neg_ms));
@@ -348,11 +396,12 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         l += (sum0 + sum1) + (sum2 + sum3);
 
-        tmem_st_x32(tS + 0, pk + 0);
-        tmem_st_x32(tS + 32, pk + 32);
+        tmem_st_x32(tS + buf * kStepN, pk);
+        if constexpr (kStepN == 128) tmem_st_x32(tS + buf * kStepN + 32, pk + 32);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + buf]);
       }
 
       // ------------------------------- epilogue: O_t / l -> bf16 -> smem -> TMA store -------------
