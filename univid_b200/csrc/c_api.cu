@@ -92,6 +92,7 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const 
 }
 
 constexpr int kFmhaStages = 4;
+constexpr int kFmhaPolyDefault = 0;
 
 template <bool kKeyMod>
 int launch_fmha(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
@@ -120,13 +121,26 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
 
-  // UVB_FMHA_STEP=64|128 selects the sub-step variant (tuning hook; default below)
+  // Tuning hooks (read once): UVB_FMHA_STEP=64|128 sub-step variant, UVB_FMHA_POLY=0|2|4 share of the
+  // exp2 evaluated on the FMA pipe (one pair in every N).
   static const int step_n = [] {
     const char* e = getenv("UVB_FMHA_STEP");
     return (e != nullptr && atoi(e) == 64) ? 64 : 128;
   }();
-  auto kern = step_n == 64 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, kKeyMod>
-                           : uvb::fmha_fwd_kernel<kFmhaStages, 128, kKeyMod>;
+  static const int poly = [] {
+    const char* e = getenv("UVB_FMHA_POLY");
+    return e != nullptr ? atoi(e) : kFmhaPolyDefault;
+  }();
+  void (*kern)(uvb::FmhaParams) = nullptr;
+  if (step_n == 64) {
+    kern = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, 2, kKeyMod>
+         : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, 4, kKeyMod>
+                     : uvb::fmha_fwd_kernel<kFmhaStages, 64, 0, kKeyMod>;
+  } else {
+    kern = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 128, 2, kKeyMod>
+         : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 128, 4, kKeyMod>
+                     : uvb::fmha_fwd_kernel<kFmhaStages, 128, 0, kKeyMod>;
+  }
   constexpr int smem = uvb::FmhaSmem<kFmhaStages>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const dim3 grid((Lq + uvb::kQTiles * uvb::kBlockM - 1) / (uvb::kQTiles * uvb::kBlockM), N, B);

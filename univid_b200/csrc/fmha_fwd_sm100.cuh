@@ -66,7 +66,42 @@ struct FmhaParams {
   float scale_log2;               // softmax_scale * log2(e)
 };
 
-template <int kStages, int kStepN, bool kKeyMod>
+// exp2 of 64 scores of one row -> 32 packed bf16x2 probabilities + partial row sums.  One pair in every
+// kPolyEvery goes through the FMA-pipe polynomial instead of MUFU.EX2 (0 = never): the XU pipe does 16
+// exp2/clk/SM, exactly the rate at which the tensor pipe consumes a 128x128 tile, so offloading a share
+// of them is what lets the softmax keep ahead of the MMAs.
+template <int kPolyEvery, bool kKeyMod>
+__device__ __forceinline__ void softmax_exp64(const uint32_t* sr, float scale_log2, float neg_ms,
+                                              float2& sum_a, float2& sum_b, uint32_t* pk,
+                                              const float* pvw) {
+  const float2 sc = make_float2(scale_log2, scale_log2);
+  const float2 nm = make_float2(neg_ms, neg_ms);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc, nm);
+    float2 e;
+    if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+      e = ex2_poly2(x);
+    } else {
+      e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+    }
+    if (i & 1) {
+      sum_b = fadd2(sum_b, e);
+    } else {
+      sum_a = fadd2(sum_a, e);
+    }
+    if constexpr (kKeyMod) {
+      if (pvw != nullptr) {
+        const float2 w = __ldg(reinterpret_cast<const float2*>(pvw) + i);
+        e.x *= w.x;
+        e.y *= w.y;
+      }
+    }
+    pk[i] = pack_bf16x2(e.x, e.y);
+  }
+}
+
+template <int kStages, int kStepN, int kPolyEvery, bool kKeyMod>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   static_assert(kStepN == 64 || kStepN == 128, "sub-step must be 64 or 128 keys");
@@ -204,15 +239,16 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       // O_t (+)= P_t[buf] V(step) : A = P from TMEM (8 columns per 16 keys), B = V rows of the step,
       // MN-major: 16 keys = 2 KiB per K-step, the two 64-dim panels are kHalfTile apart (LBO), 8-key
       // groups 1 KiB apart (SBO)
-      auto issue_pv = [&](int t, int step, int buf) {
+      auto issue_pv = [&](int t, int step, int buf, int kk0) {   // 4 K-steps = 64 keys from kk0
         const uint64_t va = v_desc + ((2 * (step / kNB) + 1) % kStages) * kTile16 + (step % kNB) * kStep16;
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
         const uint32_t a = tmem_base + t * 128 + buf * kStepN;
-        const uint32_t acc0 = step > 0 ? 1u : 0u;
+        const uint32_t acc0 = (step > 0 || kk0 > 0) ? 1u : 0u;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kStepN / 16; ++kk) {
-            umma_ts(d, a + kk * 8, va + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kk = kk0 + k4;
+            umma_ts(d, a + kk * 8, va + kk * (2048 >> 4), idesc_pv, k4 > 0 ? 1u : acc0);
           }
         }
         __syncwarp();
@@ -245,9 +281,19 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         if (buf == 0) wait_full(v_ring);                            // V tile of this step group
 #pragma unroll
         for (int t = 0; t < kQTiles; ++t) {
-          mbar_wait(&p_full[2 * t + buf], par);
-          tc_fence_after();
-          issue_pv(t, step, buf);
+          if constexpr (kNB == 1) {
+            // split-P: the first 64 keys of P_t are signalled while the softmax still works on the rest
+            mbar_wait(&p_full[2 * t + 0], par);
+            tc_fence_after();
+            issue_pv(t, step, 0, 0);
+            mbar_wait(&p_full[2 * t + 1], par);
+            tc_fence_after();
+            issue_pv(t, step, 0, 4);
+          } else {
+            mbar_wait(&p_full[2 * t + buf], par);
+            tc_fence_after();
+            issue_pv(t, step, buf, 0);
+          }
           commit(&pv_done[t]);
           if (nxt < n_steps) {
             if (t == 0 && (nxt % kNB) == 0) wait_full(k_ring);      // next K tile
@@ -366,42 +412,24 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
 
         const float neg_ms = -m * scale_log2;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-        uint32_t pk[kStepN / 2];
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
         const float* pvw = nullptr;
         if constexpr (kKeyMod) {
           if (p.key_pv_weight != nullptr) pvw = p.key_pv_weight + step * kStepN;
         }
 #pragma unroll
-        for (int c = 0; c < kStepN; c += 4) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(sr[c + 0]), scale_log2, neg_ms));
-          float e1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_ms));
-          float e2 = ex2_approx(fmaf(__uint_as_float(sr[c + 2]), scale_log2, neg_ms));
-          float e3 = ex2_approx(fmaf(__uint_as_float(sr[c + 3]), scale_log2, neg_ms));
-          sum0 += e0;
-          sum1 += e1;
-          sum2 += e2;
-          sum3 += e3;
-          if constexpr (kKeyMod) {
-            if (pvw != nullptr) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(pvw + c));
-              e0 *= w.x;
-              e1 *= w.y;
-              e2 *= w.z;
-              e3 *= w.w;
-            }
-          }
-          pk[c / 2 + 0] = pack_bf16x2(e0, e1);
-          pk[c / 2 + 1] = pack_bf16x2(e2, e3);
+        for (int h = 0; h < kStepN / 64; ++h) {
+          uint32_t pk[32];
+          softmax_exp64<kPolyEvery, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
+                                             pvw == nullptr ? nullptr : pvw + 64 * h);
+          tmem_st_x32(tS + buf * kStepN + 32 * h, pk);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          // kStepN == 128: one barrier per 64-key half (split-P); kStepN == 64: one per S buffer
+          if (lane == 0) mbar_arrive(&p_full[2 * t + (kNB == 1 ? h : buf)]);
         }
-        l += (sum0 + sum1) + (sum2 + sum3);
-
-        tmem_st_x32(tS + buf * kStepN, pk);
-        if constexpr (kStepN == 128) tmem_st_x32(tS + buf * kStepN + 32, pk + 32);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * t + buf]);
+        l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
       }
 
       // ------------------------------- epilogue: O_t / l -> bf16 -> smem -> TMA store -------------

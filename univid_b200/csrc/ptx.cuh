@@ -260,6 +260,47 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pair arithmetic (FFMA2 / FADD2 on sm_100: two lanes per instruction)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)),
+        "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {   // round towards -inf
+  float2 d;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+// 2^x for a pair on the FMA pipe (no MUFU): Cody-Waite split x = floor(x) + f via the 2^23+2^22 magic
+// constant with a round-down add, degree-3 polynomial for 2^f on [0, 1) (max rel. error 8.8e-5, far below
+// the bf16 rounding of P), exponent spliced in with an integer shift-add.  Valid for x <= 127; inputs
+// below -127 (masked keys are -inf) are clamped and come out as ~2^-127.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  constexpr float kMagic = 12582912.0f;   // 2^23 + 2^22
+  x.x = fmaxf(x.x, -127.0f);
+  x.y = fmaxf(x.y, -127.0f);
+  const float2 r = fadd2_rm(x, make_float2(kMagic, kMagic));
+  const float2 rb = fadd2(r, make_float2(-kMagic, -kMagic));
+  const float2 f = fadd2(x, make_float2(-rb.x, -rb.y));
+  float2 pl = ffma2(f, make_float2(0.077119089663028717041015625f, 0.077119089663028717041015625f),
+                    make_float2(0.227564394474029541015625f, 0.227564394474029541015625f));
+  pl = ffma2(pl, f, make_float2(0.695146143436431884765625f, 0.695146143436431884765625f));
+  pl = ffma2(pl, f, make_float2(1.0f, 1.0f));
+  return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(r.x) << 23)),
+                     __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(r.y) << 23)));
+}
 // pack two fp32 -> bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;
