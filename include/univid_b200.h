@@ -79,11 +79,24 @@ int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, in
  *   of 8 elements and every base pointer 16-byte aligned.
  *   k_lens  DEVICE int32 [B] or NULL: keys >= k_lens[b] are masked (attention.py:72-80).
  *   scale   softmax scale (reference default: 128^-0.5).
+ *   workspace, workspace_bytes   see uvb_fmha_workspace_bytes(); may be NULL / 0.
  */
 int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
                       int B, int Lq, int Lk, int N, const int64_t* q_strides,
                       const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
-                      float scale, void* stream);
+                      float scale, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Size in bytes of the scratch buffer the attention kernels use to split query blocks over the key
+ * axis when the number of 256-row query blocks is not a multiple of the SM count (the kernel is
+ * persistent, one CTA per SM; see csrc/fmha_fwd_sm100.cuh).  The caller owns the buffer: DEVICE memory,
+ * 256-byte aligned, ZERO-FILLED ONCE after allocation (the kernels leave it zero-filled where it
+ * matters), used by one stream at a time.  `workspace == NULL` is allowed everywhere and selects the
+ * schedule that never splits a query block (a partial last wave).  Returns -1 without a CUDA device. */
+int64_t uvb_fmha_workspace_bytes(void);
+
+/* Diagnostics: when set to a DEVICE buffer of (number of SMs) x 32 uint64, every attention launch records
+ * per CTA {smid, start ns, end ns of each piece of work (up to 30)} (%globaltimer).  NULL (default) = off. */
+void uvb_debug_fmha_timeline(void* device_buffer);
 
 /* Cross-attention with per-key modifiers fused (UniVid "Temperature Modality Alignment").
  * Replaces: WanCrossAttention.forward's flash_attention call (model.py:175) as entered through
@@ -100,7 +113,7 @@ int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, con
                        const float* out_bias, int B, int Lq, int Lk, int N,
                        const int64_t* q_strides, const int64_t* k_strides,
                        const int64_t* v_strides, const int64_t* o_strides, float scale,
-                       void* stream);
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(libpath):
 def test_python_binding_lists_the_same_symbols(libpath):
     from univid_b200 import _ext
     assert sorted(_ext.EXPORTS) == _declared_symbols()
-    assert _ext.lib().uvb_version() == 100
+    assert _ext.lib().uvb_version() == _ext.ABI_VERSION
     assert _ext.lib().uvb_last_error() == b""
 
 

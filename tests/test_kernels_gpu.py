@@ -38,7 +38,7 @@ def _bf16_close(got, want, frac_exact=0.98):
 @pytest.fixture(scope="module")
 def ext():
     from univid_b200 import _ext
-    assert _ext.lib().uvb_version() == 100
+    assert _ext.lib().uvb_version() == _ext.ABI_VERSION
     return _ext
 
 

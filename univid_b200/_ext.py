@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libunivid_b200.so")
 
 EXPORTS = (
     "uvb_version", "uvb_last_error", "uvb_qk_norm_rope", "uvb_head_scatter_bf16",
-    "uvb_fmha_fwd_bf16", "uvb_xattn_fwd_bf16",
+    "uvb_fmha_fwd_bf16", "uvb_fmha_workspace_bytes", "uvb_xattn_fwd_bf16", "uvb_debug_fmha_timeline",
 )
+ABI_VERSION = 101
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -41,10 +42,16 @@ def lib():
     L.uvb_head_scatter_bf16.restype = _i
     L.uvb_head_scatter_bf16.argtypes = [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp]
     L.uvb_fmha_fwd_bf16.restype = _i
-    L.uvb_fmha_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp]
+    L.uvb_fmha_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f,
+                                    _vp, _i64, _vp]
+    L.uvb_fmha_workspace_bytes.restype = _i64
+    L.uvb_fmha_workspace_bytes.argtypes = []
     L.uvb_xattn_fwd_bf16.restype = _i
     L.uvb_xattn_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
-                                     _vp, _vp, _vp, _vp, _f, _vp]
+                                     _vp, _vp, _vp, _vp, _f, _vp, _i64, _vp]
+    if L.uvb_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {L.uvb_version()}, expected {ABI_VERSION}: rebuild it "
+                           "with `python -m univid_b200.build --force`")
     _lib = L
     return L
 
@@ -188,6 +195,24 @@ def _pad128(t, lk, fill=1.0):
     return out
 
 
+_WORKSPACES = {}
+
+
+def _fmha_workspace(device, stream):
+    """Scratch buffer for the split of remainder query blocks over the key axis (uvb_fmha_workspace_bytes):
+    one per (device, stream), zero-filled once; the kernels hand it back zero-filled."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        with torch.cuda.device(device):
+            n = int(lib().uvb_fmha_workspace_bytes())
+        if n <= 0:
+            raise RuntimeError("uvb_fmha_workspace_bytes failed: " + lib().uvb_last_error().decode())
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale=None,
              key_pv_weight=None, out_bias=None):
     """softmax(q k^T * scale) v on [B, L, N, 128] bf16 tensors (any strides with contiguous head_dim).
@@ -211,8 +236,10 @@ def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale
     if k_lens is not None and (k_lens.dtype != torch.int32 or k_lens.numel() != B):
         raise ValueError("k_lens must be int32 [B] on the device")
     scale = float(D ** -0.5 if softmax_scale is None else softmax_scale)
+    stream = _stream(q)
+    ws = _fmha_workspace(q.device, stream)
     args = (B, Lq, Lk, N, _c.cast(_strides3(q), _vp), _c.cast(_strides3(k), _vp),
-            _c.cast(_strides3(v), _vp), _c.cast(_strides3(out), _vp), scale, _stream(q))
+            _c.cast(_strides3(v), _vp), _c.cast(_strides3(out), _vp), scale, ws.data_ptr(), ws.numel(), stream)
     if key_logit_scale is None and key_pv_weight is None and out_bias is None:
         _check(lib().uvb_fmha_fwd_bf16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(k_lens), *args))
     else:

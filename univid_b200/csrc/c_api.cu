@@ -91,14 +91,34 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const 
   return UVB_OK;
 }
 
+unsigned long long* g_timeline = nullptr;   // diagnostics: see uvb_debug_fmha_timeline
+
 constexpr int kFmhaStages = 4;
 constexpr int kFmhaPolyDefault = 0;
+constexpr size_t kWsFlagBytes = 4096;   // flags [sms][2] u32 live at the start of the workspace
+
+int sm_count(int* out) {
+  static int cached_dev = -1, cached = 0;
+  int dev = 0;
+  UVB_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    UVB_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  *out = cached;
+  return UVB_OK;
+}
+
+size_t fmha_ws_bytes(int sms) {
+  return kWsFlagBytes + static_cast<size_t>(sms) * uvb::kWsSlotFloats * sizeof(float);
+}
 
 template <bool kKeyMod>
 int launch_fmha(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
                 const float* key_logit_scale, const float* key_pv_weight, const float* out_bias,
                 int B, int Lq, int Lk, int N, const int64_t* qs, const int64_t* ks,
-                const int64_t* vs, const int64_t* os, float scale, void* stream) {
+                const int64_t* vs, const int64_t* os, float scale, void* workspace,
+                int64_t workspace_bytes, void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
     return fail(UVB_ERR_INVALID, "null tensor pointer");
   if (B <= 0 || Lq <= 0 || Lk <= 0 || N <= 0 || B > 65535 || N > 65535)
@@ -106,6 +126,9 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   if (!(scale > 0.f)) return fail(UVB_ERR_INVALID, "softmax scale must be positive");
   int rc = check_device();
   if (rc != UVB_OK) return rc;
+  int sms = 0;
+  if ((rc = sm_count(&sms)) != UVB_OK) return rc;
+  if (sms * 2 * sizeof(uint32_t) > kWsFlagBytes) return fail(UVB_ERR_UNSUPPORTED, "%d SMs", sms);
 
   uvb::FmhaParams p;
   memset(&p, 0, sizeof(p));
@@ -119,32 +142,46 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.out_bias = out_bias;
   p.Lq = Lq;
   p.Lk = Lk;
+  p.N = N;
+  p.n_qt = (Lq + uvb::kUnitRows - 1) / uvb::kUnitRows;
+  const long long units = static_cast<long long>(B) * N * p.n_qt;
+  if (units > 0x7fffffffLL) return fail(UVB_ERR_INVALID, "too many query blocks");
+  p.n_units = static_cast<int>(units);
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.timeline = g_timeline;
 
-  // Tuning hooks (read once): UVB_FMHA_STEP=64|128 sub-step variant, UVB_FMHA_POLY=0|2|4 share of the
-  // exp2 evaluated on the FMA pipe (one pair in every N).
-  static const int step_n = [] {
-    const char* e = getenv("UVB_FMHA_STEP");
-    return (e != nullptr && atoi(e) == 64) ? 64 : 128;
-  }();
+  // Tuning hooks (read once): UVB_FMHA_POLY=0|2|4 share of the exp2 evaluated on the FMA pipe (one pair in
+  // every N); UVB_FMHA_SPLIT=0 disables the split of the remainder units across CTAs.
   static const int poly = [] {
     const char* e = getenv("UVB_FMHA_POLY");
     return e != nullptr ? atoi(e) : kFmhaPolyDefault;
   }();
-  void (*kern)(uvb::FmhaParams) = nullptr;
-  if (step_n == 64) {
-    kern = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, 2, kKeyMod>
-         : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 64, 4, kKeyMod>
-                     : uvb::fmha_fwd_kernel<kFmhaStages, 64, 0, kKeyMod>;
-  } else {
-    kern = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 128, 2, kKeyMod>
-         : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 128, 4, kKeyMod>
-                     : uvb::fmha_fwd_kernel<kFmhaStages, 128, 0, kKeyMod>;
+  static const bool allow_split = [] {
+    const char* e = getenv("UVB_FMHA_SPLIT");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  // Persistent grid: one CTA per SM; with a workspace the remainder units are cut into equal key ranges
+  // (then even fewer units than SMs keep every SM busy).
+  const long long n_kv = (Lk + uvb::kBlockN - 1) / uvb::kBlockN;
+  long long grid_x = units < sms ? units : sms;
+  if (workspace != nullptr && allow_split) {
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+      return fail(UVB_ERR_INVALID, "workspace must be 256-byte aligned");
+    if (workspace_bytes < static_cast<int64_t>(fmha_ws_bytes(sms)))
+      return fail(UVB_ERR_INVALID, "workspace too small: %lld < %zu bytes (uvb_fmha_workspace_bytes)",
+                  static_cast<long long>(workspace_bytes), fmha_ws_bytes(sms));
+    p.flags = static_cast<uint32_t*>(workspace);
+    p.ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsFlagBytes);
+    const long long iters = units * n_kv;
+    grid_x = iters < sms ? iters : sms;
   }
+
+  void (*kern)(uvb::FmhaParams) = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 2, kKeyMod>
+                                : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 4, kKeyMod>
+                                            : uvb::fmha_fwd_kernel<kFmhaStages, 0, kKeyMod>;
   constexpr int smem = uvb::FmhaSmem<kFmhaStages>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const dim3 grid((Lq + uvb::kQTiles * uvb::kBlockM - 1) / (uvb::kQTiles * uvb::kBlockM), N, B);
-  kern<<<grid, uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  kern<<<dim3(static_cast<unsigned>(grid_x)), uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   UVB_CUDA(cudaGetLastError());
   return UVB_OK;
 }
@@ -174,7 +211,17 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 100; }
+int uvb_version(void) { return 101; }
+
+void uvb_debug_fmha_timeline(void* device_buffer) {
+  g_timeline = static_cast<unsigned long long*>(device_buffer);
+}
+
+int64_t uvb_fmha_workspace_bytes(void) {
+  int sms = 0;
+  if (sm_count(&sms) != UVB_OK) return -1;
+  return static_cast<int64_t>(fmha_ws_bytes(sms));
+}
 
 const char* uvb_last_error(void) { return g_err; }
 
@@ -261,9 +308,9 @@ int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, in
 int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
                       int B, int Lq, int Lk, int N, const int64_t* q_strides,
                       const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
-                      float scale, void* stream) {
+                      float scale, void* workspace, int64_t workspace_bytes, void* stream) {
   return launch_fmha<false>(q, k, v, o, k_lens, nullptr, nullptr, nullptr, B, Lq, Lk, N, q_strides,
-                            k_strides, v_strides, o_strides, scale, stream);
+                            k_strides, v_strides, o_strides, scale, workspace, workspace_bytes, stream);
 }
 
 int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
@@ -271,9 +318,10 @@ int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, con
                        const float* out_bias, int B, int Lq, int Lk, int N,
                        const int64_t* q_strides, const int64_t* k_strides,
                        const int64_t* v_strides, const int64_t* o_strides, float scale,
-                       void* stream) {
+                       void* workspace, int64_t workspace_bytes, void* stream) {
   return launch_fmha<true>(q, k, v, o, k_lens, key_logit_scale, key_pv_weight, out_bias, B, Lq, Lk,
-                           N, q_strides, k_strides, v_strides, o_strides, scale, stream);
+                           N, q_strides, k_strides, v_strides, o_strides, scale, workspace,
+                           workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -3,37 +3,45 @@
 // models/wan/utils/modules/attention.py:72-80) and optional per-key modifiers used by the
 // text-weighted cross-attention (reference: Wan22ContextWrapper hook, models/model_pipeline.py:1756-1803).
 //
-// Structure (one CTA per 256 query rows of one (batch, head); 3 warpgroups):
+// Work decomposition (persistent, "stream-K" over the key axis).  A *unit* is 256 query rows of one
+// (batch, head) against all keys.  The grid is one CTA per SM (G CTAs).  The U units are dealt out in
+// W = U / G full rounds (CTA g takes unit w*G + g, so concurrently running CTAs share ~1.15 heads' K/V in
+// L2 exactly like a plain grid would); the remaining R = U - W*G units are NOT a partial wave: their
+// R * n_kv key tiles are cut into G equal contiguous ranges, so every CTA does the same amount of work.
+// A unit cut across CTAs is finished by the CTA that holds its last key tile (the owner): the other
+// CTAs write their un-normalised partial (O fp32, row max, row sum) to a workspace slot and raise a
+// flag; the owner merges the partials in its epilogue.  Non-owner ranges are processed first and the
+// owner always waits on lower-numbered CTAs, so there are no wait chains.  With 1536 units on 148 SMs
+// (cfg #2) this turns 11 waves into 10.38; with 384 units (4-way Ulysses) 3 waves into 2.59.
+//
+// Inside a CTA (3 warpgroups):
 //   warps 0-3   softmax group 0  (query rows   0..127, one row per thread)   setmaxnreg.inc
 //   warps 4-7   softmax group 1  (query rows 128..255)                       setmaxnreg.inc
 //   warp  8     tcgen05.mma issuer (one elected thread) + TMEM allocator     setmaxnreg.dec
 //   warp  9     TMA producer (one elected thread)                            setmaxnreg.dec
 //   warps 10-11 idle (they only exist so the third warpgroup can give its registers away)
-// TMEM (512 columns x 128 lanes):  S0a S0b | S1a S1b | O0 | O1.  The key axis advances in 64-key
-// sub-steps and every query tile owns TWO 64-column S buffers, so the MMA thread issues
-// S_t(s+2) = Q_t K(s+2)^T right after O_t += P_t(s) V(s): while the softmax group works on step s the
-// scores of step s+1 are already (being) computed, and the softmax<->MMA hand-off is a producer/consumer
-// pipeline instead of a serial dependency chain (round-1 ncu: with one S buffer per tile the softmax warps
-// spent half their time waiting for S and the tensor pipe was 53 % busy).  P (bf16) aliases the first 32
-// columns of its S buffer and is consumed as the A operand of the PV MMA straight from TMEM.
-// K/V tiles (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem and its
+// TMEM (512 columns x 128 lanes):  S0 | S1 | O0 | O1.  P (bf16) aliases the first 64 columns of its S and
+// is consumed as the A operand of the PV MMA straight from TMEM; it is handed over in two 64-key halves
+// (split-P) so the PV MMA starts while the softmax still works on the second half.  K/V tiles
+// (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem for the segment and its
 // buffer is reused to stage O for the TMA store.
 //
 // Ordering facts the protocol relies on: tcgen05 MMAs issued by one thread execute in order, so
-// S_t(s+2) overwriting the buffer that held P_t(s) is safe once PV_t(s) has been issued before it; the
+// S_t(s+1) overwriting the buffer that held P_t(s) is safe once PV_t(s) has been issued before it; the
 // softmax warps rescale O_t in place (lazily, only when a row max grows by more than 2^8) after waiting
 // for pv_done[t] of the previous step, and PV_t(s) is not issued before they arrive on p_full[t].
+// All mbarrier parities are derived from running counters (segments, steps, ring slots) that every role
+// advances identically.
 #pragma once
 #include "ptx.cuh"
 
 namespace uvb {
 
 constexpr int kBlockM = 128;          // query rows per tile (UMMA M)
-constexpr int kBlockN = 128;          // keys per K/V smem tile (TMA granularity)
-// kStepN (template): keys per softmax/MMA sub-step (UMMA N of QK^T, K of PV): 128 -> one S buffer per
-// query tile, 64 -> two S buffers per tile (the MMA thread runs two steps ahead of the softmax)
+constexpr int kBlockN = 128;          // keys per K/V smem tile == keys per softmax/MMA step
 constexpr int kHeadDim = 128;
 constexpr int kQTiles = 2;            // query tiles per CTA
+constexpr int kUnitRows = kQTiles * kBlockM;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;   // 32 KiB, one [128 x 128] bf16 tile
 constexpr int kHalfTile = kTileBytes / 2;            // one 64-column swizzle panel
 constexpr int kFmhaThreads = 384;
@@ -41,13 +49,17 @@ constexpr int kRegsSoftmax = 224;                    // 2*128*224 + 128*56 = 645
 constexpr int kRegsOther = 56;
 constexpr float kRescaleThreshold = 8.0f;            // lazy rescale: only when max grows by > 2^8
 
+// split-unit workspace slot (one per CTA): O fp32 column-major [128 dims][256 rows], then m[256], l[256]
+constexpr int kWsOFloats = kHeadDim * kUnitRows;
+constexpr int kWsSlotFloats = kWsOFloats + 2 * kUnitRows;
+
 template <int kStages>
 struct FmhaSmem {
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQTiles * kTileBytes;
   static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
-  // barriers: q_full[2] kv_full[S] kv_empty[S] s_full[2][2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
-  static constexpr int kNumBars = 2 + 2 * kStages + 12;
+  // barriers: q_full[2] q_empty[2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
+  static constexpr int kNumBars = 4 + 2 * kStages + 10;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for 1024 B alignment
 };
@@ -61,9 +73,68 @@ struct FmhaParams {
   const float* key_logit_scale;   // [Lk] or nullptr : logits[:, j] *= key_logit_scale[j]
   const float* key_pv_weight;     // [Lk] or nullptr : P[:, j] *= w[j] after the row sum
   const float* out_bias;          // [N*128] or nullptr : added to the normalised output
+  float* ws;                      // [gridDim.x][kWsSlotFloats] or nullptr (then units are never split)
+  uint32_t* flags;                // [gridDim.x][2], zero on entry and on exit
+  unsigned long long* timeline;   // diagnostics (uvb_debug_fmha_timeline) or nullptr: per CTA 32 x u64
   int Lq;
   int Lk;
+  int n_qt;                       // 256-row query blocks per (batch, head)
+  int N;                          // heads
+  int n_units;                    // B * N * n_qt
   float scale_log2;               // softmax_scale * log2(e)
+};
+
+// One contiguous piece of work of a CTA: key tiles [a, b) of `unit`.  `owner` pieces produce the output
+// rows (after merging the partials of CTAs g-1, g-2, ... when a > 0); the others write a partial.
+struct FmhaSeg {
+  int unit, a, b;
+  bool owner;
+};
+
+// The static schedule; every role of the CTA evaluates it with identical (warp-uniform) results.
+struct FmhaSched {
+  int G, g, W, n_kv, n_seg;
+  long long rem_total;
+  FmhaSeg rem0, rem1;   // remainder pieces in processing order (non-owner first)
+
+  __device__ __forceinline__ long long rem_lo(int cta) const { return rem_total * cta / G; }
+
+  __device__ __forceinline__ void init(const FmhaParams& p, bool split) {
+    G = static_cast<int>(gridDim.x);
+    g = static_cast<int>(blockIdx.x);
+    n_kv = (p.Lk + kBlockN - 1) / kBlockN;
+    W = p.n_units / G;
+    const int R = p.n_units - W * G;
+    int n_rem = 0;
+    rem_total = 0;
+    rem0 = rem1 = FmhaSeg{0, 0, 0, true};
+    if (!split) {
+      if (g < R) {
+        rem0 = FmhaSeg{W * G + g, 0, n_kv, true};
+        n_rem = 1;
+      }
+    } else {
+      rem_total = static_cast<long long>(R) * n_kv;
+      const long long lo = rem_lo(g), hi = rem_lo(g + 1);
+      if (hi > lo) {
+        const int u0 = static_cast<int>(lo / n_kv), a0 = static_cast<int>(lo - static_cast<long long>(u0) * n_kv);
+        const int len = static_cast<int>(hi - lo);
+        if (a0 + len <= n_kv) {
+          rem0 = FmhaSeg{W * G + u0, a0, a0 + len, a0 + len == n_kv};
+          n_rem = 1;
+        } else {
+          rem0 = FmhaSeg{W * G + u0 + 1, 0, a0 + len - n_kv, false};   // head of the next unit first
+          rem1 = FmhaSeg{W * G + u0, a0, n_kv, true};
+          n_rem = 2;
+        }
+      }
+    }
+    n_seg = W + n_rem;
+  }
+  __device__ __forceinline__ FmhaSeg seg(int i) const {
+    if (i < W) return FmhaSeg{i * G + g, 0, n_kv, true};
+    return i == W ? rem0 : rem1;
+  }
 };
 
 // exp2 of 64 scores of one row -> 32 packed bf16x2 probabilities + partial row sums.  One pair in every
@@ -101,52 +172,45 @@ __device__ __forceinline__ void softmax_exp64(const uint32_t* sr, float scale_lo
   }
 }
 
-template <int kStages, int kStepN, int kPolyEvery, bool kKeyMod>
+template <int kStages, int kPolyEvery, bool kKeyMod>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
-  static_assert(kStepN == 64 || kStepN == 128, "sub-step must be 64 or 128 keys");
-  constexpr int kNB = kBlockN / kStepN;   // S buffers per query tile == sub-steps per K/V tile
   using SM = FmhaSmem<kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  // opaque to the optimiser: otherwise every mbarrier access re-derives the aligned base (S2UR CgaCtaId,
+  // SWINHI, ULEA, ... ~12 instructions each) inside the issue-sensitive softmax loop
+  asm volatile("" : "+l"(smem));
   uint8_t* smem_q = smem + SM::kQOff;
   uint8_t* smem_kv = smem + SM::kKvOff;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
-  uint64_t* q_full = bars;                       // [2]
-  uint64_t* kv_full = bars + 2;                  // [kStages]
+  uint64_t* q_full = bars;                       // [tile]   TMA -> MMA: Q_t of the segment landed
+  uint64_t* q_empty = bars + 2;                  // [tile]   softmax -> TMA: Q_t / O staging is free again
+  uint64_t* kv_full = bars + 4;                  // [kStages]
   uint64_t* kv_empty = kv_full + kStages;        // [kStages]
-  uint64_t* s_full = kv_empty + kStages;         // [tile][buffer]
-  uint64_t* p_full = s_full + 4;                 // [tile][buffer]
+  uint64_t* s_full = kv_empty + kStages;         // [tile]
+  uint64_t* p_full = s_full + 2;                 // [tile][half]
   uint64_t* pv_done = p_full + 4;                // [tile]
   uint64_t* o_full = pv_done + 2;                // [tile]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * (kQTiles * kBlockM);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-
-  int k_len = p.Lk;
-  if (p.k_lens != nullptr) k_len = min(max(p.k_lens[batch], 0), p.Lk);
-  const int n_kv = (k_len + kBlockN - 1) / kBlockN;     // K/V tiles to load
-  const int n_steps = (k_len + kStepN - 1) / kStepN;    // sub-steps
 
   if (threadIdx.x == 0) {
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&q_empty[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[2 * t], 4);       // one arrive per softmax warp
+      mbar_init(&p_full[2 * t + 1], 4);
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&o_full[t], 1);
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&s_full[2 * t + b], 1);
-        mbar_init(&p_full[2 * t + b], 4);   // one arrive per softmax warp
-      }
-      mbar_init(&pv_done[t], 1);
-      mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
   }
@@ -167,66 +231,87 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   // tcgen05 instruction in an R2UR.BROADCAST waterfall loop)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
+  FmhaSched sch;
+  sch.init(p, p.ws != nullptr);
+
+  // (batch, head, first query row) of a unit and its key-tile range clipped to the batch's key length
+  auto decode = [&](const FmhaSeg& sg, int& batch, int& head, int& q_row0, int& k_len, int& ka, int& kb) {
+    const int qt = sg.unit % p.n_qt;
+    const int bh = sg.unit / p.n_qt;
+    head = bh % p.N;
+    batch = bh / p.N;
+    q_row0 = qt * kUnitRows;
+    k_len = p.Lk;
+    if (p.k_lens != nullptr) k_len = min(max(__ldg(p.k_lens + batch), 0), p.Lk);
+    const int n_kv_b = (k_len + kBlockN - 1) / kBlockN;
+    kb = min(sg.b, n_kv_b);
+    ka = min(sg.a, kb);
+  };
+
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
-    if (n_kv > 0 && warp == 9) {
+    if (warp == 9) {
       // ===================================== TMA producer =====================================
       // the whole warp runs the loop (converged, uniform operands); one elected lane issues
-      for (int t = 0; t < kQTiles; ++t) {
-        uint8_t* dst = smem_q + t * kTileBytes;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&q_full[t], kTileBytes);
-          tma_load_4d_hint(dst, &p.tm_q, &q_full[t], 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
-          tma_load_4d_hint(dst + kHalfTile, &p.tm_q, &q_full[t], 64, q_row0 + t * kBlockM, head, batch,
-                           kEvictFirst);
+      int ring = 0;
+      for (int si = 0; si < sch.n_seg; ++si) {
+        const FmhaSeg sg = sch.seg(si);
+        int batch, head, q_row0, k_len, ka, kb;
+        decode(sg, batch, head, q_row0, k_len, ka, kb);
+        for (int t = 0; t < kQTiles; ++t) {
+          mbar_wait(&q_empty[t], (si & 1) ^ 1);
+          uint8_t* dst = smem_q + t * kTileBytes;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[t], kTileBytes);
+            tma_load_4d_hint(dst, &p.tm_q, &q_full[t], 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+            tma_load_4d_hint(dst + kHalfTile, &p.tm_q, &q_full[t], 64, q_row0 + t * kBlockM, head, batch,
+                             kEvictFirst);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      // ring order matches consumption order: K0, V0, K1, V1, ...
-      const int total = 2 * n_kv;
-      for (int i = 0; i < total; ++i) {
-        const int stage = i % kStages;
-        const uint32_t phase = (i / kStages) & 1;
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* dst = smem_kv + stage * kTileBytes;
-        const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
-        const int key0 = (i >> 1) * kBlockN;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&kv_full[stage], kTileBytes);
-          tma_load_4d_hint(dst, tm, &kv_full[stage], 0, key0, head, batch, kEvictLast);
-          tma_load_4d_hint(dst + kHalfTile, tm, &kv_full[stage], 64, key0, head, batch, kEvictLast);
+        // ring order matches consumption order: K(ka), V(ka), K(ka+1), V(ka+1), ...
+        for (int i = 2 * ka; i < 2 * kb; ++i, ++ring) {
+          const int stage = ring % kStages;
+          mbar_wait(&kv_empty[stage], ((ring / kStages) & 1) ^ 1);
+          uint8_t* dst = smem_kv + stage * kTileBytes;
+          const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
+          const int key0 = (i >> 1) * kBlockN;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&kv_full[stage], kTileBytes);
+            tma_load_4d_hint(dst, tm, &kv_full[stage], 0, key0, head, batch, kEvictLast);
+            tma_load_4d_hint(dst + kHalfTile, tm, &kv_full[stage], 64, key0, head, batch, kEvictLast);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
-    } else if (n_kv > 0 && warp == 8) {
+    } else if (warp == 8) {
       // ===================================== MMA issuer =======================================
       // The whole warp runs the control flow converged so every operand is warp-uniform; one elected
       // lane (always the same one) issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are
       // built once; per instruction only a 64-bit add of a compile-time offset remains.  (Round-1 ncu:
       // with the loop inside `if (lane == 0)` ptxas emitted an ELECT/R2UR.BROADCAST waterfall around each
       // UTCHMMA and descriptor math on the uniform datapath -- ~110 cycles per MMA, the real bottleneck.)
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kStepN, 0, 0);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
       const uint64_t q_desc = umma_desc_sw128(smem_u32(smem_q), 16, 1024);            // K-major A
       const uint64_t k_desc = umma_desc_sw128(smem_u32(smem_kv), 16, 1024);           // K-major B
       const uint64_t v_desc = umma_desc_sw128(smem_u32(smem_kv), kHalfTile, 1024);    // MN-major B
       constexpr uint64_t kTile16 = kTileBytes >> 4;           // descriptor address units are 16 B
-      constexpr uint64_t kStep16 = (kStepN * 128) >> 4;       // kStepN key rows of one 128 B panel
 
-      auto wait_full = [&](int ring) {
-        mbar_wait(&kv_full[ring % kStages], (ring / kStages) & 1);
+      auto wait_full = [&](int r) {
+        mbar_wait(&kv_full[r % kStages], (r / kStages) & 1);
         tc_fence_after();
       };
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) tc_commit(bar);
         __syncwarp();
       };
-      // S_t[buf] = Q_t K(step)^T : A, B K-major, N = kStepN keys; 8 K-steps of 16 dims: panel = kk/4,
-      // 32 B per K-step inside the 128 B swizzle atom
-      auto issue_qk = [&](int t, int step, int buf) {
+      // S_t = Q_t K^T : A, B K-major, N = 128 keys; 8 K-steps of 16 dims: panel = kk/4, 32 B per K-step
+      // inside the 128 B swizzle atom
+      auto issue_qk = [&](int t, int k_ring) {
         const uint64_t qa = q_desc + t * kTile16;
-        const uint64_t ka = k_desc + ((2 * (step / kNB)) % kStages) * kTile16 + (step % kNB) * kStep16;
-        const uint32_t d = tmem_base + t * 128 + buf * kStepN;
+        const uint64_t ka = k_desc + (k_ring % kStages) * kTile16;
+        const uint32_t d = tmem_base + t * 128;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kHeadDim / 16; ++kk) {
@@ -236,14 +321,13 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         __syncwarp();
       };
-      // O_t (+)= P_t[buf] V(step) : A = P from TMEM (8 columns per 16 keys), B = V rows of the step,
-      // MN-major: 16 keys = 2 KiB per K-step, the two 64-dim panels are kHalfTile apart (LBO), 8-key
-      // groups 1 KiB apart (SBO)
-      auto issue_pv = [&](int t, int step, int buf, int kk0) {   // 4 K-steps = 64 keys from kk0
-        const uint64_t va = v_desc + ((2 * (step / kNB) + 1) % kStages) * kTile16 + (step % kNB) * kStep16;
+      // O_t (+)= P_t V : A = P from TMEM (8 columns per 16 keys), B = V rows, MN-major: 16 keys = 2 KiB
+      // per K-step, the two 64-dim panels are kHalfTile apart (LBO), 8-key groups 1 KiB apart (SBO)
+      auto issue_pv = [&](int t, int v_ring, bool first_step, int kk0) {   // 4 K-steps = 64 keys from kk0
+        const uint64_t va = v_desc + (v_ring % kStages) * kTile16;
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
-        const uint32_t a = tmem_base + t * 128 + buf * kStepN;
-        const uint32_t acc0 = (step > 0 || kk0 > 0) ? 1u : 0u;
+        const uint32_t a = tmem_base + t * 128;
+        const uint32_t acc0 = (!first_step || kk0 > 0) ? 1u : 0u;
         if (elect_one()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -253,110 +337,111 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         __syncwarp();
       };
-      // a K/V tile is last read by its last sub-step (or by the very last step)
-      auto last_use = [&](int step) { return (step % kNB) == kNB - 1 || step == n_steps - 1; };
 
-      // prologue: scores of the first kNB steps into the S buffers of each tile
-      mbar_wait(&q_full[0], 0);
-      wait_full(0);
-      const int pre = n_steps < kNB ? n_steps : kNB;
-      for (int t = 0; t < kQTiles; ++t) {
-        if (t == 1) {
-          mbar_wait(&q_full[1], 0);
-          tc_fence_after();
+      int ring = 0;     // K/V tiles consumed so far (all segments)
+      int gstep = 0;    // softmax/MMA steps so far (all segments)
+      for (int si = 0; si < sch.n_seg; ++si) {
+        const FmhaSeg sg = sch.seg(si);
+        int batch, head, q_row0, k_len, ka, kb;
+        decode(sg, batch, head, q_row0, k_len, ka, kb);
+        const int n_steps = kb - ka;
+        mbar_wait(&q_full[0], si & 1);
+        tc_fence_after();
+        if (n_steps == 0) {
+          // nothing to attend to (k_lens clipped the range away): the epilogue treats O as zero
+          mbar_wait(&q_full[1], si & 1);
+          commit(&o_full[0]);
+          commit(&o_full[1]);
+          continue;
         }
-        for (int s0 = 0; s0 < pre; ++s0) {
-          issue_qk(t, s0, s0);
-          commit(&s_full[2 * t + s0]);
-        }
-      }
-      commit(&kv_empty[0]);   // K tile 0 is fully consumed by the prologue
+        // prologue: scores of the first step of both tiles
+        wait_full(ring);
+        issue_qk(0, ring);
+        commit(&s_full[0]);
+        mbar_wait(&q_full[1], si & 1);
+        tc_fence_after();
+        issue_qk(1, ring);
+        commit(&s_full[1]);
+        commit(&kv_empty[ring % kStages]);   // K tile of step 0 is fully consumed by the prologue
 
-      for (int step = 0; step < n_steps; ++step) {
-        const int buf = step % kNB;
-        const uint32_t par = (step / kNB) & 1;
-        const int nxt = step + kNB;
-        const int v_ring = 2 * (step / kNB) + 1;
-        const int k_ring = 2 * (nxt / kNB);
-        if (buf == 0) wait_full(v_ring);                            // V tile of this step group
+        for (int step = 0; step < n_steps; ++step) {
+          const uint32_t par = (gstep + step) & 1;
+          const int v_ring = ring + 2 * step + 1;
+          const int k_ring = v_ring + 1;          // K tile of the next step
+          const bool more = step + 1 < n_steps;
+          wait_full(v_ring);
 #pragma unroll
-        for (int t = 0; t < kQTiles; ++t) {
-          if constexpr (kNB == 1) {
+          for (int t = 0; t < kQTiles; ++t) {
             // split-P: the first 64 keys of P_t are signalled while the softmax still works on the rest
             mbar_wait(&p_full[2 * t + 0], par);
             tc_fence_after();
-            issue_pv(t, step, 0, 0);
+            issue_pv(t, v_ring, step == 0, 0);
             mbar_wait(&p_full[2 * t + 1], par);
             tc_fence_after();
-            issue_pv(t, step, 0, 4);
-          } else {
-            mbar_wait(&p_full[2 * t + buf], par);
-            tc_fence_after();
-            issue_pv(t, step, buf, 0);
+            issue_pv(t, v_ring, step == 0, 4);
+            commit(&pv_done[t]);
+            if (more) {
+              if (t == 0) wait_full(k_ring);
+              issue_qk(t, k_ring);
+              commit(&s_full[t]);
+            } else {
+              commit(&o_full[t]);
+            }
           }
-          commit(&pv_done[t]);
-          if (nxt < n_steps) {
-            if (t == 0 && (nxt % kNB) == 0) wait_full(k_ring);      // next K tile
-            issue_qk(t, nxt, buf);
-            commit(&s_full[2 * t + buf]);
-          } else if (step == n_steps - 1) {
-            commit(&o_full[t]);
-          }
+          commit(&kv_empty[v_ring % kStages]);
+          if (more) commit(&kv_empty[k_ring % kStages]);
         }
-        if (last_use(step)) commit(&kv_empty[v_ring % kStages]);
-        if (nxt < n_steps && last_use(nxt)) commit(&kv_empty[k_ring % kStages]);
+        ring += 2 * n_steps;
+        gstep += n_steps;
       }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
-    if (n_kv == 0) {
-      // No valid key: the output rows are defined as zero (flash-attn varlen convention).
-      const int t = warp >> 2;
-      const int row = (warp & 3) * 32 + lane;
-      uint8_t* so = smem_q + t * kTileBytes;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        *reinterpret_cast<uint4*>(so + (c >> 3) * kHalfTile + row * 128 + ((c & 7) << 4)) =
-            make_uint4(0, 0, 0, 0);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, kBlockM);
-      if ((warp & 3) == 0 && lane == 0) {
-        tma_store_4d(&p.tm_o, so, 0, q_row0 + t * kBlockM, head, batch);
-        tma_store_4d(&p.tm_o, so + kHalfTile, 64, q_row0 + t * kBlockM, head, batch);
-        tma_store_commit();
-        tma_store_wait0();
-      }
-    } else {
-      // ===================================== softmax groups ====================================
-      const int t = warp >> 2;
-      const int wq = warp & 3;
-      const int row = wq * 32 + lane;
-      const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-      const uint32_t tS = tmem_base + lane_addr + t * 128;
-      const uint32_t tO = tmem_base + lane_addr + 256 + t * kHeadDim;
-      const float scale_log2 = p.scale_log2;
+    // ===================================== softmax groups ====================================
+    const int t = warp >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + t * 128;
+    const uint32_t tO = tmem_base + lane_addr + 256 + t * kHeadDim;
+    const float scale_log2 = p.scale_log2;
+    const int ws_row = t * kBlockM + row;          // row inside the unit
+    bool stored = false;
+    int gstep = 0;
+    if (p.timeline != nullptr && threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.timeline[blockIdx.x * 32 + 0] = smid;
+      p.timeline[blockIdx.x * 32 + 1] = globaltimer_ns();
+    }
+
+    for (int si = 0; si < sch.n_seg; ++si) {
+      if (p.timeline != nullptr && threadIdx.x == 0 && si > 0 && si < 30)
+        p.timeline[blockIdx.x * 32 + 1 + si] = globaltimer_ns();
+      const FmhaSeg sg = sch.seg(si);
+      int batch, head, q_row0, k_len, ka, kb;
+      decode(sg, batch, head, q_row0, k_len, ka, kb);
+      const int n_steps = kb - ka;
       float m = -INFINITY;  // running row max in raw-logit units
       float l = 0.f;        // running row sum of exp2((s - m) * scale_log2)
 
       for (int step = 0; step < n_steps; ++step) {
-        const int buf = step % kNB;
-        mbar_wait(&s_full[2 * t + buf], (step / kNB) & 1);
+        const uint32_t par = (gstep + step) & 1;
+        const int key0 = (ka + step) * kBlockN;
+        mbar_wait(&s_full[t], par);
         tc_fence_after();
-        uint32_t sr[kStepN];
-        tmem_ld_x32(tS + buf * kStepN, sr);
-        tmem_ld_x32(tS + buf * kStepN + 32, sr + 32);
-        if constexpr (kStepN == 128) {
-          tmem_ld_x32(tS + buf * kStepN + 64, sr + 64);
-          tmem_ld_x32(tS + buf * kStepN + 96, sr + 96);
-        }
+        uint32_t sr[kBlockN];
+        tmem_ld_x32(tS, sr);
+        tmem_ld_x32(tS + 32, sr + 32);
+        tmem_ld_x32(tS + 64, sr + 64);
+        tmem_ld_x32(tS + 96, sr + 96);
         tmem_wait_ld();
 
         if constexpr (kKeyMod) {
           if (p.key_logit_scale != nullptr) {
-            const float4* ks = reinterpret_cast<const float4*>(p.key_logit_scale + step * kStepN);
+            const float4* ks = reinterpret_cast<const float4*>(p.key_logit_scale + key0);
 #pragma unroll
-            for (int c = 0; c < kStepN / 4; ++c) {
+            for (int c = 0; c < kBlockN / 4; ++c) {
               // entries past Lk are masked below; the host pads the array to a multiple of 128
               const float4 w = __ldg(ks + c);
               sr[4 * c + 0] = __float_as_uint(__uint_as_float(sr[4 * c + 0]) * w.x);
@@ -366,10 +451,10 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             }
           }
         }
-        const int valid = k_len - step * kStepN;
-        if (valid < kStepN) {
+        const int valid = k_len - key0;   // only the last key tile of a sequence can be ragged
+        if (valid < kBlockN) {
 #pragma unroll
-          for (int c = 0; c < kStepN; ++c) {
+          for (int c = 0; c < kBlockN; ++c) {
             if (c >= valid) sr[c] = 0xff800000u;  // -inf
           }
         }
@@ -377,7 +462,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
         float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
 #pragma unroll
-        for (int c = 4; c < kStepN; c += 4) {
+        for (int c = 4; c < kBlockN; c += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
           mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
@@ -392,7 +477,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           if (__any_sync(0xffffffffu, need)) {
             // O_t may still be accumulating PV_t(step-1): wait for it.  PV_t(step) cannot be issued
             // before we arrive on p_full below, so pv_done[t] is at most one phase ahead of us.
-            mbar_wait(&pv_done[t], (step - 1) & 1);
+            mbar_wait(&pv_done[t], par ^ 1);
             tc_fence_after();
             const float m_new = fmaxf(m, tile_max);
             const float f = ex2_approx((m - m_new) * scale_log2);
@@ -415,42 +500,123 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
         const float* pvw = nullptr;
         if constexpr (kKeyMod) {
-          if (p.key_pv_weight != nullptr) pvw = p.key_pv_weight + step * kStepN;
+          if (p.key_pv_weight != nullptr) pvw = p.key_pv_weight + key0;
         }
 #pragma unroll
-        for (int h = 0; h < kStepN / 64; ++h) {
+        for (int h = 0; h < 2; ++h) {
           uint32_t pk[32];
           softmax_exp64<kPolyEvery, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
                                              pvw == nullptr ? nullptr : pvw + 64 * h);
-          tmem_st_x32(tS + buf * kStepN + 32 * h, pk);
+          tmem_st_x32(tS + 32 * h, pk);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          // kStepN == 128: one barrier per 64-key half (split-P); kStepN == 64: one per S buffer
-          if (lane == 0) mbar_arrive(&p_full[2 * t + (kNB == 1 ? h : buf)]);
+          if (lane == 0) mbar_arrive(&p_full[2 * t + h]);   // one barrier per 64-key half (split-P)
         }
         l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
       }
+      gstep += n_steps;
 
-      // ------------------------------- epilogue: O_t / l -> bf16 -> smem -> TMA store -------------
-      mbar_wait(&o_full[t], 0);
+      // ------------------------------------- segment epilogue -------------------------------------
+      mbar_wait(&o_full[t], si & 1);
       tc_fence_after();
-      const float inv = 1.0f / l;
+      const bool have_o = n_steps > 0;     // otherwise TMEM holds stale data and O is zero
+
+      if (!sg.owner) {
+        // ---- partial: un-normalised O (fp32, column-major so a warp writes 128 contiguous bytes), m, l
+        float* slot = p.ws + static_cast<size_t>(sch.g) * kWsSlotFloats;
+        if (have_o) {
+#pragma unroll
+          for (int c = 0; c < kHeadDim / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld_x32(tO + c * 32, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) __stcg(slot + (c * 32 + i) * kUnitRows + ws_row, __uint_as_float(orr[i]));
+          }
+        }
+        __stcg(slot + kWsOFloats + ws_row, m);
+        __stcg(slot + kWsOFloats + kUnitRows + ws_row, have_o ? l : 0.f);
+        __threadfence();
+        tc_fence_before();
+        named_bar_sync(1 + t, kBlockM);
+        if (wq == 0 && lane == 0) {
+          st_release_gpu(p.flags + 2 * sch.g + t, 1u);
+          mbar_arrive(&q_empty[t]);
+        }
+        continue;
+      }
+
+      // ---- owner: merge the partials of the CTAs that hold key tiles [0, a) of this unit
+      float m_tot = have_o ? m : -INFINITY;
+      int g_lo = sch.g;   // parts come from CTAs [g_lo, g)
+      if (sg.a > 0) {
+        const long long unit_lo = static_cast<long long>(sg.unit - sch.W * sch.G) * sch.n_kv;
+        while (g_lo > 0 && sch.rem_lo(g_lo) > unit_lo) --g_lo;
+        for (int gp = g_lo; gp < sch.g; ++gp) {
+          if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;     // that CTA has no remainder range
+          const uint32_t* flag = p.flags + 2 * gp + t;
+          if (ld_acquire_gpu(flag) == 0u) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(flag) == 0u) {
+              if (clock64() - t0 > 8000000000LL) __trap();
+            }
+          }
+          const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+          if (__ldcg(slot + kWsOFloats + kUnitRows + ws_row) > 0.f)
+            m_tot = fmaxf(m_tot, __ldcg(slot + kWsOFloats + ws_row));
+        }
+      }
+      const float alpha = (have_o && sg.a > 0) ? ex2_approx((m - m_tot) * scale_log2) : 1.0f;
+      float l_tot = have_o ? l * alpha : 0.f;
+      if (sg.a > 0) {
+        for (int gp = g_lo; gp < sch.g; ++gp) {
+          if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;
+          const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+          const float lp = __ldcg(slot + kWsOFloats + kUnitRows + ws_row);
+          if (lp > 0.f) l_tot += lp * ex2_approx((__ldcg(slot + kWsOFloats + ws_row) - m_tot) * scale_log2);
+        }
+      }
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      const float own_scale = alpha * inv;
+
       uint8_t* so = smem_q + t * kTileBytes;  // Q_t is dead once o_full[t] has fired
       const float* bias = nullptr;
       if constexpr (kKeyMod) {
-        if (p.out_bias != nullptr) bias = p.out_bias + head * kHeadDim;
+        if (p.out_bias != nullptr && l_tot > 0.f) bias = p.out_bias + head * kHeadDim;
       }
-  #pragma unroll
+#pragma unroll
       for (int c = 0; c < kHeadDim / 32; ++c) {
         uint32_t orr[32];
-        tmem_ld_x32(tO + c * 32, orr);
-        tmem_wait_ld();
+        if (have_o) {
+          tmem_ld_x32(tO + c * 32, orr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * own_scale);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) orr[i] = 0u;
+        }
+        if (sg.a > 0) {
+          for (int gp = g_lo; gp < sch.g; ++gp) {
+            if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;
+            const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+            const float lp = __ldcg(slot + kWsOFloats + kUnitRows + ws_row);
+            if (lp > 0.f) {
+              const float w = ex2_approx((__ldcg(slot + kWsOFloats + ws_row) - m_tot) * scale_log2) * inv;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                orr[i] = __float_as_uint(fmaf(__ldcg(slot + (c * 32 + i) * kUnitRows + ws_row), w,
+                                              __uint_as_float(orr[i])));
+              }
+            }
+          }
+        }
         uint32_t ob[16];
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = __uint_as_float(orr[2 * i]) * inv;
-          float b = __uint_as_float(orr[2 * i + 1]) * inv;
+          float a = __uint_as_float(orr[2 * i]);
+          float b = __uint_as_float(orr[2 * i + 1]);
           if constexpr (kKeyMod) {
             if (bias != nullptr) {
               a += __ldg(bias + c * 32 + 2 * i);
@@ -461,7 +627,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         // 32 columns = 4 x 16-byte chunks of panel (c/2); SWIZZLE_128B: chunk ^= row % 8
         uint8_t* prow = so + (c >> 1) * kHalfTile + row * 128;
-  #pragma unroll
+#pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int chunk = (c & 1) * 4 + q4;
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
@@ -469,14 +635,25 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
       }
       fence_proxy_async_smem();
+      tc_fence_before();
       named_bar_sync(1 + t, kBlockM);
       if (wq == 0 && lane == 0) {
         tma_store_4d(&p.tm_o, so, 0, q_row0 + t * kBlockM, head, batch);
         tma_store_4d(&p.tm_o, so + kHalfTile, 64, q_row0 + t * kBlockM, head, batch);
         tma_store_commit();
-        tma_store_wait0();
+        if (sg.a > 0) {   // every thread of the group has read the partials: hand the slots back
+          for (int gp = g_lo; gp < sch.g; ++gp) {
+            if (sch.rem_lo(gp + 1) != sch.rem_lo(gp)) st_release_gpu(p.flags + 2 * gp + t, 0u);
+          }
+        }
+        tma_store_wait_read0();          // the staging buffer may be overwritten by the next Q_t
+        mbar_arrive(&q_empty[t]);
+        stored = true;
       }
     }
+    if (stored) tma_store_wait0();
+    if (p.timeline != nullptr && threadIdx.x == 0)
+      p.timeline[blockIdx.x * 32 + 1 + min(sch.n_seg, 30)] = globaltimer_ns();
   }
 
   // ------------------------------------------ teardown ------------------------------------------
