@@ -225,6 +225,10 @@ def run_native_arm(args, cfg_key):
     grid = [(f, h, w)]
     seq_lens = torch.tensor([L])
     fmha_events, prol_events = [], []
+    ctx = None
+    if world > 1:
+        p2p = importlib.import_module("univid_b200.wan.distributed.p2p")
+        ctx = p2p.context(1, s, heads, dev)
 
     def kernel_step(record):
         """P + S + X of every layer through the C ABI; with world > 1 the Ulysses exchange around S."""
@@ -242,6 +246,14 @@ def run_native_arm(args, cfg_key):
                     ev[2].record()
                     prol_events.append((ev[0], ev[1]))
                     fmha_events.append((ev[1], ev[2]))
+            elif ctx is not None:
+                # fused exchange: producers store into the peers' buffers, attention stores o into the owners'
+                ctx.next_epoch()
+                _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid,
+                                  tok_offset=rank * s, groups=world,
+                                  peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
+                _ext.head_scatter(t["v"], world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
+                ctx.attend(None)
             else:
                 q_send, k_send = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs,
                                                    grid_sizes=grid, tok_offset=rank * s, groups=world)
@@ -377,7 +389,9 @@ def run_native_arm(args, cfg_key):
             "config": {"workload": cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, "
                        "512-key cross-attention) of all layers", "video_tokens": L, "text_tokens": text_len,
                        "dim": dim, "heads": heads, "layers": layers,
-                       "sharding": "none" if world == 1 else f"Ulysses heads/{world} over NCCL all-to-all",
+                       "sharding": "none" if world == 1 else (
+                           f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
+                           if ctx is not None else f"Ulysses heads/{world} over NCCL all-to-all"),
                        "l2_policy": "inputs larger than L2: 4 rotating layer-input sets of "
                                     f"{3 * s * dim * 2 / 1e6:.0f} MB each"},
             "attention_flop_per_step": flop_step,

@@ -94,6 +94,51 @@ int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, cons
  * schedule that never splits a query block (a partial last wave).  Returns -1 without a CUDA device. */
 int64_t uvb_fmha_workspace_bytes(void);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused Ulysses exchange over NVLink peer memory (replaces: all_to_all() x4 in distributed_attention,
+ * models/wan/distributed/ulysses.py:32-46 / util.py:21-31, and the grouped p2p it issues through NCCL).
+ * One process per GPU.  Every rank owns an exchange buffer (uvb_sp_buffer_alloc), exports it
+ * (uvb_sp_ipc_export), and maps every peer's (uvb_sp_ipc_import).  The producers then store q/k/v head
+ * groups straight into the destination rank's buffer (uvb_qk_norm_rope_sp, uvb_head_scatter_sp), the
+ * attention kernel TMA-stores each output tile into the buffer of the rank that owns its tokens
+ * (uvb_fmha_fwd_sp_bf16), and two flag kernels order producers and consumers across GPUs: uvb_sp_signal
+ * after a producer, uvb_sp_wait before the consumer, with one monotonically increasing value per exchange.
+ * No NCCL call and no pack/unpack pass remains on the data path.
+ *
+ * uvb_sp_buffer_alloc is the only call in this library that allocates device memory (cudaMalloc: IPC needs
+ * a whole allocation) and synchronises; it is a set-up call, not on the hot path.  Handles are 64 bytes.
+ */
+int uvb_sp_buffer_alloc(int64_t bytes, void** dev_ptr);     /* zero-filled */
+int uvb_sp_buffer_free(void* dev_ptr);
+int uvb_sp_ipc_export(void* dev_ptr, void* handle64);
+int uvb_sp_ipc_import(const void* handle64, void** peer_ptr);
+int uvb_sp_ipc_close(void* peer_ptr);
+/* flag_ptrs: HOST array of n DEVICE pointers (this rank's flag word inside each peer's buffer): after all
+ * work queued on `stream` so far, *flag_ptrs[i] = value (system-scope release). */
+int uvb_sp_signal(void* const* flag_ptrs, int n, uint32_t value, void* stream);
+/* flags: DEVICE uint32[n] in this rank's buffer: work queued on `stream` afterwards starts only once every
+ * flags[i] - value >= 0 (wrap-safe).  Traps after ~10 s instead of hanging the GPU. */
+int uvb_sp_wait(const void* flags, int n, uint32_t value, void* stream);
+
+/* uvb_qk_norm_rope with peer stores: with n_peers = p > 0 (N == hpg * p) head group j of element (b, l) goes
+ * to {q,k}_peers[j] + b*out_sb + l*out_sl + (n % hpg)*128 + d; {q,k}_peers are HOST arrays of p DEVICE
+ * pointers, q_out/k_out/out_sg are ignored.  n_peers == 0 is uvb_qk_norm_rope. */
+int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const float* wq,
+                        const float* wk, const float* cos_sin, const float* row_scale,
+                        const float* pre_bias, void* q_out, void* k_out, void* const* q_peers,
+                        void* const* k_peers, int n_peers, int B, int L, int N,
+                        const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
+                        int64_t out_sl, int64_t out_sg, void* stream);
+int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n_peers, int B, int L,
+                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream);
+/* uvb_fmha_fwd_bf16 on a head shard [B, Lq, N, 128] whose output rows [j*Lq/p, (j+1)*Lq/p) are stored into
+ * rank j's buffer o_peers[j] = [B, Lq/p, total_heads, 128] at heads [head_offset, head_offset + N). */
+int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,
+                         int head_offset, int total_heads, const int32_t* k_lens, int B, int Lq, int Lk,
+                         int N, const int64_t* q_strides, const int64_t* k_strides,
+                         const int64_t* v_strides, float scale, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
 /* Diagnostics: when set to a DEVICE buffer of (number of SMs) x 32 uint64, every attention launch records
  * per CTA {smid, start ns, end ns of each piece of work (up to 30)} (%globaltimer).  NULL (default) = off. */
 void uvb_debug_fmha_timeline(void* device_buffer);

@@ -14,8 +14,11 @@ LIB_PATH = os.path.join(_HERE, "libunivid_b200.so")
 EXPORTS = (
     "uvb_version", "uvb_last_error", "uvb_qk_norm_rope", "uvb_head_scatter_bf16",
     "uvb_fmha_fwd_bf16", "uvb_fmha_workspace_bytes", "uvb_xattn_fwd_bf16", "uvb_debug_fmha_timeline",
+    "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
+    "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
+    "uvb_sp_wait",
 )
-ABI_VERSION = 101
+ABI_VERSION = 102
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -49,6 +52,29 @@ def lib():
     L.uvb_xattn_fwd_bf16.restype = _i
     L.uvb_xattn_fwd_bf16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                      _vp, _vp, _vp, _vp, _f, _vp, _i64, _vp]
+    _u32, _pp = _c.c_uint32, _c.POINTER(_c.c_void_p)
+    L.uvb_qk_norm_rope_sp.restype = _i
+    L.uvb_qk_norm_rope_sp.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                      _vp, _i, _f, _i, _i64, _i64, _i64, _vp]
+    L.uvb_head_scatter_sp.restype = _i
+    L.uvb_head_scatter_sp.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp]
+    L.uvb_fmha_fwd_sp_bf16.restype = _i
+    L.uvb_fmha_fwd_sp_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f,
+                                       _vp, _i64, _vp]
+    L.uvb_sp_buffer_alloc.restype = _i
+    L.uvb_sp_buffer_alloc.argtypes = [_i64, _pp]
+    L.uvb_sp_buffer_free.restype = _i
+    L.uvb_sp_buffer_free.argtypes = [_vp]
+    L.uvb_sp_ipc_export.restype = _i
+    L.uvb_sp_ipc_export.argtypes = [_vp, _vp]
+    L.uvb_sp_ipc_import.restype = _i
+    L.uvb_sp_ipc_import.argtypes = [_vp, _pp]
+    L.uvb_sp_ipc_close.restype = _i
+    L.uvb_sp_ipc_close.argtypes = [_vp]
+    L.uvb_sp_signal.restype = _i
+    L.uvb_sp_signal.argtypes = [_vp, _i, _u32, _vp]
+    L.uvb_sp_wait.restype = _i
+    L.uvb_sp_wait.argtypes = [_vp, _i, _u32, _vp]
     if L.uvb_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB_PATH} has ABI version {L.uvb_version()}, expected {ABI_VERSION}: rebuild it "
                            "with `python -m univid_b200.build --force`")
@@ -124,10 +150,17 @@ def _grouped_strides(o, groups):
     return o.stride(1), o.stride(2), o.stride(0)
 
 
+def ptr_array(ptrs):
+    """ctypes void*[n] from a list of integer device addresses (kept alive by the caller)."""
+    return (_c.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
 def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=None, tok_offset=0,
-                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None):
+                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None, peers=None):
     """Fused RMSNorm (+RoPE) of q and/or k: [B, L, dim] -> bf16 [B, L, N, 128] (groups == 1) or the
-    Ulysses send layout [groups, B, L, N/groups, 128].  See uvb_qk_norm_rope in the header."""
+    Ulysses send layout [groups, B, L, N/groups, 128].  See uvb_qk_norm_rope in the header.
+    peers = (q_ptrs, k_ptrs, out_sb, out_sl): head group j is stored through q_ptrs[j] / k_ptrs[j]
+    (ctypes void*[groups] of peer-mapped device addresses, uvb_qk_norm_rope_sp) and nothing is returned."""
     global launch_count
     ref = q_in if q_in is not None else k_in
     _require_cuda(q_in, k_in, wq, wk, cos_sin, row_scale, pre_bias)
@@ -145,6 +178,23 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
         if t is not None and (t.dtype != dt or not t.is_contiguous() or t.shape != ref.shape):
             raise RuntimeError("q_in / k_in must be contiguous, same shape and dtype")
     hpg = N // groups
+    if peers is not None:
+        q_ptrs, k_ptrs, out_sb, out_sl = peers
+        grid = None
+        if cos_sin is not None:
+            grid, key = _grid_array(grid_sizes)
+            if len(key) != B:
+                raise ValueError("grid_sizes must have one (f, h, w) row per sample")
+        f32 = lambda t: None if t is None else (t if t.dtype == torch.float32 else t.float()).contiguous()
+        wq, wk, row_scale, pre_bias = f32(wq), f32(wk), f32(row_scale), f32(pre_bias)
+        _check(lib().uvb_qk_norm_rope_sp(
+            _ptr(q_in), _ptr(k_in), UVB_BF16 if dt == torch.bfloat16 else UVB_F32, _ptr(wq), _ptr(wk),
+            _ptr(cos_sin), _ptr(row_scale), _ptr(pre_bias), None, None,
+            None if q_in is None else _c.cast(q_ptrs, _vp), None if k_in is None else _c.cast(k_ptrs, _vp),
+            groups, B, L, N, None if grid is None else _c.cast(grid, _vp), int(tok_offset), float(eps), hpg,
+            int(out_sb), int(out_sl), 0, _stream(ref)))
+        launch_count += 1
+        return None, None
     q_out = _grouped_out(q_out, q_in, groups, B, L, hpg, ref.device)
     k_out = _grouped_out(k_out, k_in, groups, B, L, hpg, ref.device)
     strides = _grouped_strides(q_out if q_out is not None else k_out, groups)
@@ -166,14 +216,21 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
     return q_out, k_out
 
 
-def head_scatter(v, groups, out=None):
-    """v [B, L, N, 128] bf16 -> [groups, B, L, N/groups, 128] (Ulysses send layout)."""
+def head_scatter(v, groups, out=None, peers=None):
+    """v [B, L, N, 128] bf16 -> [groups, B, L, N/groups, 128] (Ulysses send layout); with
+    peers = (ptrs, out_sb, out_sl) head group j is stored through ptrs[j] (uvb_head_scatter_sp)."""
     global launch_count
     _require_cuda(v)
     B, L, N, D = v.shape
     if D != 128 or v.dtype != torch.bfloat16 or not v.is_contiguous():
         raise RuntimeError("head_scatter expects contiguous bf16 [B, L, N, 128]")
     hpg = N // groups
+    if peers is not None:
+        ptrs, out_sb, out_sl = peers
+        _check(lib().uvb_head_scatter_sp(_ptr(v), None, _c.cast(ptrs, _vp), groups, B, L, N, hpg, int(out_sb),
+                                         int(out_sl), 0, _stream(v)))
+        launch_count += 1
+        return None
     out = _grouped_out(out, v, groups, B, L, hpg, v.device)
     sb, sl, sg = _grouped_strides(out, groups)
     _check(lib().uvb_head_scatter_bf16(_ptr(v), _ptr(out), B, L, N, hpg, sb, sl, sg, _stream(v)))
@@ -251,3 +308,41 @@ def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale
                                         _ptr(pvw), _ptr(ob), *args))
     launch_count += 1
     return out
+
+
+def fmha_fwd_sp(q, k, v, o_ptrs, n_peers, head_offset, total_heads, k_lens=None, softmax_scale=None):
+    """Attention on a head shard q/k/v [B, L, n, 128] whose output rows are TMA-stored into the ranks that own
+    them: rows [j*L/p, (j+1)*L/p) -> o_ptrs[j] = [B, L/p, total_heads, 128] at heads [head_offset, +n)
+    (uvb_fmha_fwd_sp_bf16)."""
+    global launch_count
+    _require_cuda(q, k, v, k_lens)
+    _no_grad_only(q, k, v)
+    B, Lq, N, D = q.shape
+    Lk = k.shape[1]
+    if D != 128 or k.shape != (B, Lk, N, D) or v.shape != (B, Lk, N, D):
+        raise NotImplementedError("fmha_fwd_sp: q/k/v must be [B, L, n, 128] with equal head counts")
+    for t in (q, k, v):
+        if t.dtype != torch.bfloat16:
+            raise NotImplementedError(f"fmha_fwd_sp computes in bf16; got {t.dtype}")
+    if k_lens is not None and (k_lens.dtype != torch.int32 or k_lens.numel() != B):
+        raise ValueError("k_lens must be int32 [B] on the device")
+    scale = float(D ** -0.5 if softmax_scale is None else softmax_scale)
+    stream = _stream(q)
+    ws = _fmha_workspace(q.device, stream)
+    _check(lib().uvb_fmha_fwd_sp_bf16(
+        _ptr(q), _ptr(k), _ptr(v), _c.cast(o_ptrs, _vp), int(n_peers), int(head_offset), int(total_heads),
+        _ptr(k_lens), B, Lq, Lk, N, _c.cast(_strides3(q), _vp), _c.cast(_strides3(k), _vp),
+        _c.cast(_strides3(v), _vp), scale, ws.data_ptr(), ws.numel(), stream))
+    launch_count += 1
+
+
+def sp_signal(flag_ptrs, n, value, stream):
+    global launch_count
+    _check(lib().uvb_sp_signal(_c.cast(flag_ptrs, _vp), int(n), int(value) & 0xffffffff, stream))
+    launch_count += 1
+
+
+def sp_wait(flags_ptr, n, value, stream):
+    global launch_count
+    _check(lib().uvb_sp_wait(int(flags_ptr), int(n), int(value) & 0xffffffff, stream))
+    launch_count += 1

@@ -118,9 +118,12 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
                 const float* key_logit_scale, const float* key_pv_weight, const float* out_bias,
                 int B, int Lq, int Lk, int N, const int64_t* qs, const int64_t* ks,
                 const int64_t* vs, const int64_t* os, float scale, void* workspace,
-                int64_t workspace_bytes, void* stream) {
-  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
+                int64_t workspace_bytes, void* stream, void* const* o_peers = nullptr, int n_peers = 0,
+                int head_offset = 0, int total_heads = 0) {
+  if (q == nullptr || k == nullptr || v == nullptr || (o == nullptr && n_peers == 0))
     return fail(UVB_ERR_INVALID, "null tensor pointer");
+  if (n_peers < 0 || n_peers > uvb::kMaxPeers || (n_peers > 0 && (o_peers == nullptr || Lq % n_peers != 0)))
+    return fail(UVB_ERR_INVALID, "bad peer list (n_peers=%d, Lq=%d)", n_peers, Lq);
   if (B <= 0 || Lq <= 0 || Lk <= 0 || N <= 0 || B > 65535 || N > 65535)
     return fail(UVB_ERR_INVALID, "bad shape B=%d Lq=%d Lk=%d N=%d", B, Lq, Lk, N);
   if (!(scale > 0.f)) return fail(UVB_ERR_INVALID, "softmax scale must be positive");
@@ -135,7 +138,19 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   if ((rc = make_tile_map(&p.tm_q, q, B, Lq, N, qs)) != UVB_OK) return rc;
   if ((rc = make_tile_map(&p.tm_k, k, B, Lk, N, ks)) != UVB_OK) return rc;
   if ((rc = make_tile_map(&p.tm_v, v, B, Lk, N, vs)) != UVB_OK) return rc;
-  if ((rc = make_tile_map(&p.tm_o, o, B, Lq, N, os)) != UVB_OK) return rc;
+  if (n_peers == 0) {
+    if ((rc = make_tile_map(&p.tm_o, o, B, Lq, N, os)) != UVB_OK) return rc;
+  } else {
+    // rank j owns output rows [j*chunk, (j+1)*chunk): its buffer is [B, chunk, total_heads, 128]
+    if (total_heads < head_offset + N) return fail(UVB_ERR_INVALID, "head_offset + N > total_heads");
+    p.n_peers = n_peers;
+    p.chunk = Lq / n_peers;
+    p.o_head_off = head_offset;
+    for (int j = 0; j < n_peers; ++j) {
+      if (o_peers[j] == nullptr) return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
+      if ((rc = make_tile_map(&p.tm_o_peer[j], o_peers[j], B, p.chunk, total_heads, nullptr)) != UVB_OK) return rc;
+    }
+  }
   p.k_lens = k_lens;
   p.key_logit_scale = key_logit_scale;
   p.key_pv_weight = key_pv_weight;
@@ -186,8 +201,8 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   return UVB_OK;
 }
 
-template <typename InT>
-int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
+template <typename InT, bool kPeers>
+int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
   const long long units = 2LL * p.B * p.L;   // one warp group per (row, q|k)
   const dim3 block(uvb::kNormRopeWarps * 32);
   auto blocks = [&](int wpr) {
@@ -196,22 +211,27 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
   };
   const int dim = p.N * 128;
   switch (dim) {   // VPL * WPR = dim / 256
-    case 1536: uvb::qk_norm_rope_kernel<InT, 6, 1><<<blocks(1), block, 0, stream>>>(p); break;
-    case 2048: uvb::qk_norm_rope_kernel<InT, 8, 1><<<blocks(1), block, 0, stream>>>(p); break;
-    case 3072: uvb::qk_norm_rope_kernel<InT, 6, 2><<<blocks(2), block, 0, stream>>>(p); break;
-    case 4096: uvb::qk_norm_rope_kernel<InT, 8, 2><<<blocks(2), block, 0, stream>>>(p); break;
-    case 5120: uvb::qk_norm_rope_kernel<InT, 5, 4><<<blocks(4), block, 0, stream>>>(p); break;
-    default: uvb::qk_norm_rope_kernel<InT, 0, 1><<<blocks(1), block, 0, stream>>>(p); break;
+    case 1536: uvb::qk_norm_rope_kernel<InT, 6, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
+    case 2048: uvb::qk_norm_rope_kernel<InT, 8, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
+    case 3072: uvb::qk_norm_rope_kernel<InT, 6, 2, kPeers><<<blocks(2), block, 0, stream>>>(p); break;
+    case 4096: uvb::qk_norm_rope_kernel<InT, 8, 2, kPeers><<<blocks(2), block, 0, stream>>>(p); break;
+    case 5120: uvb::qk_norm_rope_kernel<InT, 5, 4, kPeers><<<blocks(4), block, 0, stream>>>(p); break;
+    default: uvb::qk_norm_rope_kernel<InT, 0, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
   }
   UVB_CUDA(cudaGetLastError());
   return UVB_OK;
+}
+
+template <typename InT>
+int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
+  return p.n_peers > 0 ? launch_norm_rope_t<InT, true>(p, stream) : launch_norm_rope_t<InT, false>(p, stream);
 }
 
 }  // namespace
 
 extern "C" {
 
-int uvb_version(void) { return 101; }
+int uvb_version(void) { return 102; }
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -230,9 +250,26 @@ int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const flo
                      const float* pre_bias, void* q_out, void* k_out, int B, int L, int N,
                      const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
                      int64_t out_sl, int64_t out_sg, void* stream) {
+  return uvb_qk_norm_rope_sp(q_in, k_in, in_dtype, wq, wk, cos_sin, row_scale, pre_bias, q_out, k_out,
+                             nullptr, nullptr, 0, B, L, N, grid_fhw, tok_offset, eps, hpg, out_sb, out_sl,
+                             out_sg, stream);
+}
+
+int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const float* wq,
+                        const float* wk, const float* cos_sin, const float* row_scale,
+                        const float* pre_bias, void* q_out, void* k_out, void* const* q_peers,
+                        void* const* k_peers, int n_peers, int B, int L, int N,
+                        const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
+                        int64_t out_sl, int64_t out_sg, void* stream) {
   if (q_in == nullptr && k_in == nullptr) return fail(UVB_ERR_INVALID, "q_in and k_in are both null");
-  if ((q_in != nullptr && q_out == nullptr) || (k_in != nullptr && k_out == nullptr))
+  if (n_peers < 0 || n_peers > uvb::kMaxPeers) return fail(UVB_ERR_INVALID, "n_peers=%d", n_peers);
+  if (n_peers > 0) {
+    if (hpg <= 0 || N != hpg * n_peers) return fail(UVB_ERR_INVALID, "N=%d != hpg=%d * n_peers=%d", N, hpg, n_peers);
+    if ((q_in != nullptr && q_peers == nullptr) || (k_in != nullptr && k_peers == nullptr))
+      return fail(UVB_ERR_INVALID, "missing peer pointer list");
+  } else if ((q_in != nullptr && q_out == nullptr) || (k_in != nullptr && k_out == nullptr)) {
     return fail(UVB_ERR_INVALID, "missing output pointer");
+  }
   if (B <= 0 || L <= 0 || N <= 0) return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d", B, L, N);
   if (in_dtype != UVB_BF16 && in_dtype != UVB_F32) return fail(UVB_ERR_INVALID, "bad in_dtype %d", in_dtype);
   if (hpg <= 0 || N % hpg != 0) return fail(UVB_ERR_INVALID, "hpg=%d must divide N=%d", hpg, N);
@@ -276,15 +313,29 @@ int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const flo
   p.out_sb = out_sb;
   p.out_sl = out_sl;
   p.out_sg = out_sg;
+  p.n_peers = n_peers;
+  for (int j = 0; j < n_peers; ++j) {
+    p.q_peer[j] = q_in != nullptr ? static_cast<__nv_bfloat16*>(q_peers[j]) : nullptr;
+    p.k_peer[j] = k_in != nullptr ? static_cast<__nv_bfloat16*>(k_peers[j]) : nullptr;
+    if ((q_in != nullptr && p.q_peer[j] == nullptr) || (k_in != nullptr && p.k_peer[j] == nullptr))
+      return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return in_dtype == UVB_BF16 ? launch_norm_rope<__nv_bfloat16>(p, st) : launch_norm_rope<float>(p, st);
 }
 
 int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, int hpg,
                           int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream) {
-  if (v_in == nullptr || v_out == nullptr) return fail(UVB_ERR_INVALID, "null pointer");
+  return uvb_head_scatter_sp(v_in, v_out, nullptr, 0, B, L, N, hpg, out_sb, out_sl, out_sg, stream);
+}
+
+int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n_peers, int B, int L,
+                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream) {
+  if (v_in == nullptr || (v_out == nullptr && n_peers == 0)) return fail(UVB_ERR_INVALID, "null pointer");
   if (B <= 0 || L <= 0 || N <= 0 || hpg <= 0 || N % hpg != 0)
     return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d hpg=%d", B, L, N, hpg);
+  if (n_peers < 0 || n_peers > uvb::kMaxPeers || (n_peers > 0 && (peers == nullptr || N != hpg * n_peers)))
+    return fail(UVB_ERR_INVALID, "bad peer list (n_peers=%d)", n_peers);
   int rc = check_device();
   if (rc != UVB_OK) return rc;
   uvb::HeadScatterParams p;
@@ -297,6 +348,11 @@ int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, in
   p.out_sb = out_sb;
   p.out_sl = out_sl;
   p.out_sg = out_sg;
+  p.n_peers = n_peers;
+  for (int j = 0; j < n_peers; ++j) {
+    if (peers[j] == nullptr) return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
+    p.peer[j] = static_cast<__nv_bfloat16*>(peers[j]);
+  }
   const long long total = static_cast<long long>(B) * L * N * 16;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
@@ -311,6 +367,75 @@ int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, cons
                       float scale, void* workspace, int64_t workspace_bytes, void* stream) {
   return launch_fmha<false>(q, k, v, o, k_lens, nullptr, nullptr, nullptr, B, Lq, Lk, N, q_strides,
                             k_strides, v_strides, o_strides, scale, workspace, workspace_bytes, stream);
+}
+
+int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,
+                         int head_offset, int total_heads, const int32_t* k_lens, int B, int Lq, int Lk,
+                         int N, const int64_t* q_strides, const int64_t* k_strides,
+                         const int64_t* v_strides, float scale, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  if (n_peers <= 0) return fail(UVB_ERR_INVALID, "n_peers must be positive");
+  return launch_fmha<false>(q, k, v, nullptr, k_lens, nullptr, nullptr, nullptr, B, Lq, Lk, N, q_strides,
+                            k_strides, v_strides, nullptr, scale, workspace, workspace_bytes, stream,
+                            o_peers, n_peers, head_offset, total_heads);
+}
+
+// ------------------------------- exchange buffers, IPC, hand-off flags -------------------------------
+int uvb_sp_buffer_alloc(int64_t bytes, void** dev_ptr) {
+  if (bytes <= 0 || dev_ptr == nullptr) return fail(UVB_ERR_INVALID, "bad arguments");
+  UVB_CUDA(cudaMalloc(dev_ptr, static_cast<size_t>(bytes)));
+  UVB_CUDA(cudaMemset(*dev_ptr, 0, static_cast<size_t>(bytes)));
+  UVB_CUDA(cudaDeviceSynchronize());
+  return UVB_OK;
+}
+
+int uvb_sp_buffer_free(void* dev_ptr) {
+  UVB_CUDA(cudaFree(dev_ptr));
+  return UVB_OK;
+}
+
+int uvb_sp_ipc_export(void* dev_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (dev_ptr == nullptr || handle64 == nullptr) return fail(UVB_ERR_INVALID, "null pointer");
+  cudaIpcMemHandle_t h;
+  UVB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return UVB_OK;
+}
+
+int uvb_sp_ipc_import(const void* handle64, void** peer_ptr) {
+  if (handle64 == nullptr || peer_ptr == nullptr) return fail(UVB_ERR_INVALID, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  UVB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return UVB_OK;
+}
+
+int uvb_sp_ipc_close(void* peer_ptr) {
+  UVB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return UVB_OK;
+}
+
+int uvb_sp_signal(void* const* flag_ptrs, int n, uint32_t value, void* stream) {
+  if (flag_ptrs == nullptr || n <= 0 || n > uvb::kMaxPeers) return fail(UVB_ERR_INVALID, "bad flag list");
+  uvb::SpSignalParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n; ++i) {
+    if (flag_ptrs[i] == nullptr) return fail(UVB_ERR_INVALID, "null flag pointer %d", i);
+    p.flag[i] = static_cast<uint32_t*>(flag_ptrs[i]);
+  }
+  p.n = n;
+  p.value = value;
+  uvb::sp_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
+}
+
+int uvb_sp_wait(const void* flags, int n, uint32_t value, void* stream) {
+  if (flags == nullptr || n <= 0 || n > 32) return fail(UVB_ERR_INVALID, "bad flag array");
+  uvb::sp_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(flags), n, value);
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
 }
 
 int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,

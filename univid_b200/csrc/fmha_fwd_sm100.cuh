@@ -76,6 +76,13 @@ struct FmhaParams {
   float* ws;                      // [gridDim.x][kWsSlotFloats] or nullptr (then units are never split)
   uint32_t* flags;                // [gridDim.x][2], zero on entry and on exit
   unsigned long long* timeline;   // diagnostics (uvb_debug_fmha_timeline) or nullptr: per CTA 32 x u64
+  // Fused Ulysses output exchange: when n_peers > 0 the rows [j*chunk, (j+1)*chunk) of the output belong
+  // to rank j and are TMA-stored straight into rank j's [B, chunk, N_total, 128] buffer (tm_o_peer[j],
+  // mapped over NVLink) at head offset o_head_off; tm_o is unused.
+  int n_peers;
+  int chunk;
+  int o_head_off;
+  CUtensorMap tm_o_peer[8];
   int Lq;
   int Lk;
   int n_qt;                       // 256-row query blocks per (batch, head)
@@ -222,7 +229,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     tma_prefetch_desc(&p.tm_q);
     tma_prefetch_desc(&p.tm_k);
     tma_prefetch_desc(&p.tm_v);
-    tma_prefetch_desc(&p.tm_o);
+    if (p.n_peers == 0) tma_prefetch_desc(&p.tm_o);
   }
   tc_fence_before();
   __syncthreads();
@@ -638,8 +645,19 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       tc_fence_before();
       named_bar_sync(1 + t, kBlockM);
       if (wq == 0 && lane == 0) {
-        tma_store_4d(&p.tm_o, so, 0, q_row0 + t * kBlockM, head, batch);
-        tma_store_4d(&p.tm_o, so + kHalfTile, 64, q_row0 + t * kBlockM, head, batch);
+        const int r0 = q_row0 + t * kBlockM;
+        if (p.n_peers == 0) {
+          tma_store_4d(&p.tm_o, so, 0, r0, head, batch);
+          tma_store_4d(&p.tm_o, so + kHalfTile, 64, r0, head, batch);
+        } else {
+          // the tile may straddle two (or more) ranks' token chunks: one clipped store per rank (rows
+          // outside [0, chunk) of a rank's map are out of bounds and dropped by the TMA unit)
+          const int j_last = min((r0 + kBlockM - 1) / p.chunk, p.n_peers - 1);
+          for (int j = r0 / p.chunk; j <= j_last; ++j) {
+            tma_store_4d(&p.tm_o_peer[j], so, 0, r0 - j * p.chunk, p.o_head_off + head, batch);
+            tma_store_4d(&p.tm_o_peer[j], so + kHalfTile, 64, r0 - j * p.chunk, p.o_head_off + head, batch);
+          }
+        }
         tma_store_commit();
         if (sg.a > 0) {   // every thread of the group has read the partials: hand the slots back
           for (int gp = g_lo; gp < sch.g; ++gp) {

@@ -17,6 +17,7 @@
 namespace uvb {
 
 constexpr int kMaxBatchGrid = 8;
+constexpr int kMaxPeers = 8;     // ranks of one NVSwitch box
 
 struct NormRopeParams {
   const void* q_in;        // [B, L, dim]  (InT)
@@ -35,6 +36,11 @@ struct NormRopeParams {
   // output addressing: elem(b, l, n, d) = b*out_sb + l*out_sl + (n / hpg)*out_sg + (n % hpg)*128 + d
   int hpg;                 // heads per group (N for plain [B,L,N,128])
   long long out_sb, out_sl, out_sg;
+  // Ulysses peer stores: when n_peers > 0 head group j is written through {q,k}_peer[j] (a pointer into
+  // rank j's exchange buffer, mapped over NVLink) instead of {q,k}_out + j*out_sg
+  int n_peers;
+  __nv_bfloat16* q_peer[kMaxPeers];
+  __nv_bfloat16* k_peer[kMaxPeers];
 };
 
 template <typename InT>
@@ -95,7 +101,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // pre-map x <- rscale * x + pre_bias (text-weighted context rows).
 template <typename InT, int VPL, int WPR, bool kPre>
 __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const float* __restrict__ w,
-                                              __nv_bfloat16* __restrict__ out_row, int hpg,
+                                              __nv_bfloat16* __restrict__ out_row,
+                                              __nv_bfloat16* const* peers, long long out_off, int hpg,
                                               long long out_sg, int dim, float eps, bool rotate,
                                               const float (&cs)[8], float rscale,
                                               const float* __restrict__ pre_bias, int lane,
@@ -142,7 +149,7 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
   // w == nullptr: qk_norm disabled (nn.Identity, model.py:123-124) -> rotation only
   const bool normed = w != nullptr;
   const float rinv = normed ? rsqrtf(ss / static_cast<float>(dim) + eps) : 1.0f;
-  const bool flat = hpg * 128 == dim;   // one head group: output rows are dense [N, 128]
+  const bool flat = hpg * 128 == dim && peers == nullptr;   // one head group: output rows are dense [N, 128]
 
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -181,7 +188,11 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
     } else {
       const int n = vec >> 4;                  // head index
       const int d0 = (vec & 15) * 8;           // offset inside the head
-      dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+      if (peers != nullptr) {
+        dst = peers[n / hpg] + out_off + (n % hpg) * 128 + d0;      // rank (n / hpg)'s buffer, over NVLink
+      } else {
+        dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+      }
     }
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o[0]),
                  "r"(o[1]), "r"(o[2]), "r"(o[3])
@@ -194,8 +205,9 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
 template <typename InT>
 __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in,
                                                       const float* __restrict__ w,
-                                                      __nv_bfloat16* __restrict__ out_row, int hpg,
-                                                      long long out_sg, int dim, float eps,
+                                                      __nv_bfloat16* __restrict__ out_row,
+                                                      __nv_bfloat16* const* peers, long long out_off,
+                                                      int hpg, long long out_sg, int dim, float eps,
                                                       bool rotate, const float (&cs)[8],
                                                       float rscale,
                                                       const float* __restrict__ pre_bias, int lane) {
@@ -254,7 +266,9 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
     }
     const int n = vec >> 4;
     const int d0 = (vec & 15) * 8;
-    __nv_bfloat16* dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+    __nv_bfloat16* dst = peers != nullptr
+                             ? peers[n / hpg] + out_off + (n % hpg) * 128 + d0
+                             : out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
     *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -264,7 +278,7 @@ constexpr int kNormRopeWarps = 8;
 // One group of WPR warps per (token row, tensor): even groups take q, odd groups k, so the groups of a
 // token sit next to each other and share the token's (cos, sin) lines in L1.
 // VPL * WPR = dim / 256 (16-byte vectors per lane); VPL == 0 selects the generic two-pass path.
-template <typename InT, int VPL, int WPR>
+template <typename InT, int VPL, int WPR, bool kPeers>
 __global__ void __launch_bounds__(kNormRopeWarps * 32, sizeof(InT) == 2 ? 3 : 2)
 qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
   __shared__ float red[kNormRopeWarps];
@@ -310,19 +324,20 @@ qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
   const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
   const float* w = is_k ? p.wk : p.wq;
   __nv_bfloat16* dst = (is_k ? p.k_out : p.q_out) + out_off;
+  __nv_bfloat16* const* peers = kPeers ? (is_k ? p.k_peer : p.q_peer) : nullptr;
   const float* pre_bias = is_k ? p.pre_bias : nullptr;
   const float rscale = (is_k && p.row_scale != nullptr) ? p.row_scale[l] : 1.0f;
   if constexpr (VPL > 0) {
     if (pre_bias != nullptr) {
-      norm_rope_row<InT, VPL, WPR, true>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
-                                         rscale, pre_bias, lane, red + group * WPR, 1 + group);
+      norm_rope_row<InT, VPL, WPR, true>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
+                                         rotate, cs, rscale, pre_bias, lane, red + group * WPR, 1 + group);
     } else {
-      norm_rope_row<InT, VPL, WPR, false>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
-                                          rscale, nullptr, lane, red + group * WPR, 1 + group);
+      norm_rope_row<InT, VPL, WPR, false>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
+                                          rotate, cs, rscale, nullptr, lane, red + group * WPR, 1 + group);
     }
   } else {
-    norm_rope_row_generic<InT>(src + in_off, w, dst, p.hpg, p.out_sg, dim, p.eps, rotate, cs, rscale,
-                               pre_bias, lane);
+    norm_rope_row_generic<InT>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
+                               rscale, pre_bias, lane);
   }
 }
 
@@ -332,6 +347,8 @@ struct HeadScatterParams {
   __nv_bfloat16* out;
   int B, L, N, hpg;
   long long out_sb, out_sl, out_sg;
+  int n_peers;                              // > 0: group j goes through peer[j] (see NormRopeParams)
+  __nv_bfloat16* peer[kMaxPeers];
 };
 
 __global__ void __launch_bounds__(256) head_scatter_kernel(const __grid_constant__ HeadScatterParams p) {
@@ -344,10 +361,45 @@ __global__ void __launch_bounds__(256) head_scatter_kernel(const __grid_constant
     const int b = static_cast<int>(row / p.L), l = static_cast<int>(row % p.L);
     const int n = vec >> 4, d0 = (vec & 15) * 8;
     const uint4 val = __ldg(reinterpret_cast<const uint4*>(p.in) + i);
-    __nv_bfloat16* dst = p.out + b * p.out_sb + l * p.out_sl +
-                         static_cast<long long>(n / p.hpg) * p.out_sg + (n % p.hpg) * 128 + d0;
+    __nv_bfloat16* base = p.n_peers > 0 ? p.peer[n / p.hpg]
+                                        : p.out + static_cast<long long>(n / p.hpg) * p.out_sg;
+    __nv_bfloat16* dst = base + b * p.out_sb + l * p.out_sl + (n % p.hpg) * 128 + d0;
     *reinterpret_cast<uint4*>(dst) = val;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Cross-GPU hand-off flags of the fused Ulysses exchange.  A producer kernel's remote stores are followed
+// (in stream order) by sp_signal_kernel, which publishes `value` into a flag word in every peer's buffer;
+// the consumer runs sp_wait_kernel before the kernel that reads what the peers wrote.  Values only grow
+// (one epoch per exchange), so nothing is ever reset.
+// ----------------------------------------------------------------------------------------------
+struct SpSignalParams {
+  uint32_t* flag[kMaxPeers];   // flag word of this rank inside each peer's flag array
+  int n;
+  uint32_t value;
+};
+
+__global__ void sp_signal_kernel(const __grid_constant__ SpSignalParams p) {
+  if (threadIdx.x < p.n) {
+    __threadfence_system();
+    st_release_sys(p.flag[threadIdx.x], p.value);
+  }
+}
+
+// Spins until every flags[i] >= value (wrap-safe).  Bounded: after ~10 s without progress the kernel
+// traps (reported by the host as a launch failure) instead of hanging the GPU.
+__global__ void sp_wait_kernel(const uint32_t* flags, int n, uint32_t value) {
+  if (threadIdx.x < n) {
+    const uint32_t* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
+      if (clock64() - t0 > 20000000000LL) __trap();
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 }  // namespace uvb

@@ -1,0 +1,150 @@
+"""Fused Ulysses exchange over NVLink peer memory (the B200-native replacement of the four NCCL
+all-to-alls per layer in models/wan/distributed/ulysses.py:32-46).
+
+Every rank owns one exchange buffer (allocated and IPC-exported through the C ABI, include/univid_b200.h
+`uvb_sp_*`) laid out as
+
+    flags (4 KiB) | q_recv | k_recv | v_recv  each [B, p, s, n, 128]  ==  [B, L, n, 128]
+                  | o_recv                         [B, s, N, 128]
+
+with p ranks, s = L/p local tokens, n = N/p local heads.  Rank i's producer kernels (q/k RMSNorm+RoPE
+prologue, v head scatter) store head group j directly into slot (b, i) of rank j's q/k/v_recv; rank j's
+attention kernel reads [B, L, n, 128] in place and TMA-stores each output tile into o_recv of the rank that
+owns its tokens, at head offset j*n.  Two flag words per peer pair order producers and consumers
+(`uvb_sp_signal` / `uvb_sp_wait`); the value is the exchange counter, identical on all ranks because every
+rank executes the same sequence of layers.  No NCCL call, no pack/unpack pass and no intermediate copy is
+left on the data path; torch.distributed is used once, to swap the 64-byte IPC handles.
+
+Buffer reuse is safe without double buffering: a rank only starts the producers of exchange e+1 after it
+has waited for every peer's o-signal of exchange e (so all attention kernels that read q/k/v_recv are done),
+and peers only store o of exchange e+1 after this rank's qkv-signal e+1, which it issues after consuming
+o_recv of exchange e (same stream).  `attend()` therefore returns a VIEW of o_recv that must be consumed on
+the current stream before the next exchange (the o projection does exactly that).
+"""
+import ctypes
+import os
+import warnings
+
+import torch
+import torch.distributed as dist
+
+from ... import _ext
+
+_FLAG_BYTES = 4096
+_O_FLAG_OFF = 128          # bytes: qkv flags at [0, 4p), o flags at [128, 128 + 4p)
+_CONTEXTS = {}
+_DISABLED = None
+
+
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier so torch can alias memory the C ABI allocated."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class UlyssesP2P:
+    def __init__(self, B, s, N, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        p = self.world
+        if N % p != 0:
+            raise ValueError(f"{N} heads cannot be split over {p} ranks")
+        self.B, self.s, self.N, self.n, self.L = B, s, N, N // p, p * s
+        self.device = device
+        elems = B * s * N * 128                       # == B * L * n * 128
+        self.off_q = _FLAG_BYTES
+        self.off_k = self.off_q + _align(elems * 2)
+        self.off_v = self.off_k + _align(elems * 2)
+        self.off_o = self.off_v + _align(elems * 2)
+        self.nbytes = self.off_o + _align(elems * 2)
+        lib = _ext.lib()
+        with torch.cuda.device(device):
+            base = ctypes.c_void_p()
+            _ext._check(lib.uvb_sp_buffer_alloc(self.nbytes, ctypes.byref(base)))
+            self.base = int(base.value)
+            handle = ctypes.create_string_buffer(64)
+            _ext._check(lib.uvb_sp_ipc_export(self.base, handle))
+            handles = [None] * p
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.peer_base = []
+            for j in range(p):
+                if j == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                ptr = ctypes.c_void_p()
+                _ext._check(lib.uvb_sp_ipc_import(ctypes.create_string_buffer(handles[j], 64), ctypes.byref(ptr)))
+                self.peer_base.append(int(ptr.value))
+        n, r = self.n, self.rank
+        slot = r * s * n * 128 * 2                    # byte offset of slot (b = 0, i = rank) in a peer's q/k/v_recv
+        self.q_peers = _ext.ptr_array([pb + self.off_q + slot for pb in self.peer_base])
+        self.k_peers = _ext.ptr_array([pb + self.off_k + slot for pb in self.peer_base])
+        self.v_peers = _ext.ptr_array([pb + self.off_v + slot for pb in self.peer_base])
+        self.o_peers = _ext.ptr_array([pb + self.off_o for pb in self.peer_base])
+        self.qkv_flag_peers = _ext.ptr_array([pb + 4 * r for pb in self.peer_base])
+        self.o_flag_peers = _ext.ptr_array([pb + _O_FLAG_OFF + 4 * r for pb in self.peer_base])
+        self.send_sb, self.send_sl = p * s * n * 128, n * 128      # element strides of a slot inside [B, p, s, n, 128]
+        raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=device)
+        self._raw = raw
+        view = lambda off, shape: raw[off:off + elems * 2].view(torch.bfloat16).view(shape)
+        self.q_local = view(self.off_q, (B, self.L, n, 128))
+        self.k_local = view(self.off_k, (B, self.L, n, 128))
+        self.v_local = view(self.off_v, (B, self.L, n, 128))
+        self.o_local = view(self.off_o, (B, s, N, 128))
+        self.epoch = 0
+        dist.barrier(group=group)                      # every rank has mapped every buffer
+
+    # ---- the exchange, in stream order ----------------------------------------------------------------
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
+
+    def qkv_ready(self, stream):
+        """After the producers: publish, then wait for every rank's q/k/v slots of this exchange."""
+        _ext.sp_signal(self.qkv_flag_peers, self.world, self.epoch, stream)
+        _ext.sp_wait(self.base, self.world, self.epoch, stream)
+
+    def o_ready(self, stream):
+        _ext.sp_signal(self.o_flag_peers, self.world, self.epoch, stream)
+        _ext.sp_wait(self.base + _O_FLAG_OFF, self.world, self.epoch, stream)
+
+    def attend(self, k_lens=None):
+        """q/k/v_recv (filled by the producers of this exchange) -> view of o_recv [B, s, N, 128]."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.qkv_ready(stream)
+        _ext.fmha_fwd_sp(self.q_local, self.k_local, self.v_local, self.o_peers, self.world, self.rank * self.n,
+                         self.N, k_lens=k_lens)
+        self.o_ready(stream)
+        return self.o_local
+
+
+def context(B, s, N, device, group=None):
+    """The (cached) exchange context for this shape, or None when the peer path is unavailable
+    (UVB_SP_P2P=0, or CUDA IPC refused in this environment -> NCCL all-to-all is used instead)."""
+    global _DISABLED
+    if _DISABLED is None:
+        _DISABLED = os.environ.get("UVB_SP_P2P", "1") == "0"
+    if _DISABLED:
+        return None
+    key = (B, s, N, device.index, id(group))
+    ctx = _CONTEXTS.get(key)
+    if ctx is None:
+        ok = torch.ones(1, device=device)
+        try:
+            ctx = UlyssesP2P(B, s, N, device, group)
+        except RuntimeError as e:          # IPC not permitted (container without shared IPC namespace, ...)
+            warnings.warn(f"univid_b200: NVLink peer exchange unavailable ({e}); using NCCL all-to-all")
+            ok.zero_()
+            ctx = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # all ranks take the same path
+        if ok.item() == 0:
+            ctx = None
+            _DISABLED = True
+        _CONTEXTS[key] = ctx
+    return ctx

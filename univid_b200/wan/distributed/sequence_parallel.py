@@ -2,14 +2,19 @@
 WanSelfAttention / WanModel instances with types.MethodType when use_sp=True
 (textimage2video.py:143-147).
 
-sp_attn_forward is the multi-GPU hot path: the fused prologue kernel normalises, rotates (with the
-rank's token offset) and stores q and k straight into the Ulysses send layout; v is scattered by a
-copy kernel; three all-to-alls, the attention kernel on [B, L, N/p, 128], one all-to-all back.
+sp_attn_forward is the multi-GPU hot path.  Default (NVLink peer memory, wan/distributed/p2p.py): the fused
+prologue kernel normalises, rotates (with the rank's token offset) and stores every head group of q and k
+straight into the exchange buffer of the rank that owns it, v is scattered the same way by a copy kernel,
+the attention kernel reads [B, L, N/p, 128] in place and TMA-stores each output tile into the rank that
+owns its tokens; flag kernels order the GPUs.  Without CUDA IPC (or with UVB_SP_P2P=0) the same producers
+write local send buffers and the exchange is three NCCL all-to-alls in and one out.
 """
 import torch
 
 from ... import _ext
 from ..modules.model import _cos_sin_table, sinusoidal_embedding_1d  # noqa: F401
+from . import p2p
+from ..modules.attention import _k_lens_arg
 from .ulysses import attend_exchanged, distributed_attention  # noqa: F401
 from .util import gather_forward, get_rank, get_world_size
 
@@ -79,11 +84,18 @@ def sp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16):
         return type(self).forward(self, x, seq_lens, grid_sizes, freqs)
     if n % world != 0:
         raise ValueError(f'{n} heads cannot be split over {world} ranks')
-    q_send, k_send = self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes,
-                                    tok_offset=rank * s, groups=world)
     v = self.v(x).view(b, s, n, d)
     if v.dtype != torch.bfloat16:
         v = v.to(torch.bfloat16)
+    ctx = p2p.context(b, s, n, x.device)
+    if ctx is not None:
+        ctx.next_epoch()
+        self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes, tok_offset=rank * s,
+                       groups=world, peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
+        _ext.head_scatter(v.contiguous(), world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
+        return self._out_proj(ctx.attend(_k_lens_arg(seq_lens, b, world * s, x.device)))
+    q_send, k_send = self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes,
+                                    tok_offset=rank * s, groups=world)
     v_send = _ext.head_scatter(v.contiguous(), world)
     x = attend_exchanged(q_send, k_send, v_send, seq_lens)
     return self._out_proj(x)

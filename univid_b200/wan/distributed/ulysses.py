@@ -70,5 +70,15 @@ def distributed_attention(
         return flash_attention(q, k, v, k_lens=seq_lens)
     if q.size(2) % world != 0:
         raise ValueError(f'{q.size(2)} heads cannot be split over {world} ranks')
+    from . import p2p
+    b, s, n, d = q.shape
+    ctx = p2p.context(b, s, n, q.device) if (d == 128 and k.shape == q.shape and v.shape == q.shape) else None
+    if ctx is not None:
+        ctx.next_epoch()
+        for t, ptrs in ((q, ctx.q_peers), (k, ctx.k_peers), (v, ctx.v_peers)):
+            t = t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+            _ext.head_scatter(t.contiguous(), world, peers=(ptrs, ctx.send_sb, ctx.send_sl))
+        x = ctx.attend(_k_lens_arg(seq_lens, b, world * s, q.device))
+        return x.to(out_dtype, copy=True)      # o_recv is reused by the next exchange
     x = attend_exchanged(pack_heads(q, world), pack_heads(k, world), pack_heads(v, world), seq_lens)
     return x.type(out_dtype)
