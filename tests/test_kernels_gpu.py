@@ -180,3 +180,55 @@ def test_unsupported_shapes_raise(ext):
     q = torch.zeros(1, 8, 2, 128, dtype=torch.float16, device="cuda")
     with pytest.raises(NotImplementedError):
         ext.fmha_fwd(q, q, q)
+
+
+@pytest.mark.parametrize("p,s,heads,batch", [(2, 120, 4, 1), (4, 60, 4, 1), (2, 256, 2, 2), (8, 45, 8, 1), (2, 130, 6, 1)])
+def test_sp_kernels_with_local_peers(ext, p, s, heads, batch):
+    """The fused Ulysses exchange kernels (uvb_*_sp) on ONE GPU: the p 'peer' buffers are p local buffers, and the
+    p ranks run one after the other.  Checks the peer-store addressing of the prologue / head scatter, the
+    per-rank clipped TMA stores of the attention epilogue (tiles straddling token chunks), and the flag kernels,
+    against the plain kernels on the unsharded problem."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(p * 1000 + s)
+    n, L, dim = heads // p, p * s, heads * 128
+    bf = torch.bfloat16
+    q_lin = torch.randn(batch, L, dim, generator=g).to(bf).to(dev)
+    k_lin = torch.randn(batch, L, dim, generator=g).to(bf).to(dev)
+    v = torch.randn(batch, L, heads, 128, generator=g).to(bf).to(dev)
+    wq = (1 + 0.1 * torch.randn(dim, generator=g)).to(dev)
+    wk = (1 + 0.1 * torch.randn(dim, generator=g)).to(dev)
+    _, cs = _cos_sin(dev)
+    f = 2
+    grid = [(f, 5, (L - 7) // (f * 5))] * batch                     # a few trailing padding tokens
+    k_lens = torch.tensor([L - 3] * batch, dtype=torch.int32, device=dev)
+    # unsharded reference through the plain kernels
+    q_ref, k_ref = ext.qk_norm_rope(q_lin, k_lin, wq, wk, 1e-6, heads, cos_sin=cs, grid_sizes=grid)
+    o_ref = ext.fmha_fwd(q_ref, k_ref, v, k_lens=k_lens)
+    # "rank" j's buffers: q/k/v_recv [B, p, s, n, 128] == [B, L, n, 128]; o_recv [B, s, N, 128]
+    recv = [{t: torch.zeros(batch, L, n, 128, dtype=bf, device=dev) for t in "qkv"} for _ in range(p)]
+    o_recv = [torch.full((batch, s, heads, 128), float("nan"), dtype=bf, device=dev) for _ in range(p)]
+    flags = torch.zeros(p, 32, dtype=torch.int32, device=dev)
+    send_sb, send_sl = p * s * n * 128, n * 128
+    stream = torch.cuda.current_stream().cuda_stream
+    for i in range(p):                                               # producers of rank i
+        sl = slice(i * s, (i + 1) * s)
+        off = i * s * n * 128 * 2
+        qp = ext.ptr_array([recv[j]["q"].data_ptr() + off for j in range(p)])
+        kp = ext.ptr_array([recv[j]["k"].data_ptr() + off for j in range(p)])
+        vp = ext.ptr_array([recv[j]["v"].data_ptr() + off for j in range(p)])
+        ext.qk_norm_rope(q_lin[:, sl].contiguous(), k_lin[:, sl].contiguous(), wq, wk, 1e-6, heads, cos_sin=cs,
+                         grid_sizes=grid, tok_offset=i * s, groups=p, peers=(qp, kp, send_sb, send_sl))
+        ext.head_scatter(v[:, sl].contiguous(), p, peers=(vp, send_sb, send_sl))
+        ext.sp_signal(ext.ptr_array([flags[j].data_ptr() + 4 * i for j in range(p)]), p, 7, stream)
+    for j in range(p):                                               # consumer of rank j
+        ext.sp_wait(flags[j].data_ptr(), p, 7, stream)
+        hs = slice(j * n, (j + 1) * n)
+        assert torch.equal(recv[j]["q"], q_ref[:, :, hs]), "q exchange"
+        assert torch.equal(recv[j]["k"], k_ref[:, :, hs]), "k exchange"
+        assert torch.equal(recv[j]["v"], v[:, :, hs]), "v exchange"
+        ext.fmha_fwd_sp(recv[j]["q"], recv[j]["k"], recv[j]["v"], ext.ptr_array([o.data_ptr() for o in o_recv]), p,
+                        j * n, heads, k_lens=k_lens)
+    torch.cuda.synchronize()
+    got = torch.cat(o_recv, dim=1)                                   # [B, L, N, 128]
+    assert torch.isfinite(got.float()).all(), "an output row was not written"
+    assert torch.equal(got, o_ref)

@@ -146,8 +146,10 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     p.n_peers = n_peers;
     p.chunk = Lq / n_peers;
     p.o_head_off = head_offset;
+    p.o_heads = total_heads;
     for (int j = 0; j < n_peers; ++j) {
       if (o_peers[j] == nullptr) return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
+      p.o_peer_ptr[j] = static_cast<__nv_bfloat16*>(o_peers[j]);
       if ((rc = make_tile_map(&p.tm_o_peer[j], o_peers[j], B, p.chunk, total_heads, nullptr)) != UVB_OK) return rc;
     }
   }

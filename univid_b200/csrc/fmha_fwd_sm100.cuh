@@ -82,6 +82,8 @@ struct FmhaParams {
   int n_peers;
   int chunk;
   int o_head_off;
+  int o_heads;                    // total heads of the peers' [B, chunk, o_heads, 128] buffers
+  __nv_bfloat16* o_peer_ptr[8];
   CUtensorMap tm_o_peer[8];
   int Lq;
   int Lk;
@@ -588,6 +590,21 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       const float own_scale = alpha * inv;
 
       uint8_t* so = smem_q + t * kTileBytes;  // Q_t is dead once o_full[t] has fired
+      // Peer mode: a tile whose 128 rows lie in ONE rank's token chunk is TMA-stored into that rank's
+      // buffer; a tile that straddles chunks is written row by row with plain stores (each thread owns a
+      // row and picks its rank) -- TMA rejects the negative start coordinate a clipped store would need.
+      const int r0 = q_row0 + t * kBlockM;
+      const int j_first = p.n_peers > 0 ? r0 / p.chunk : 0;
+      const bool direct = p.n_peers > 0 && r0 + kBlockM > (j_first + 1) * p.chunk && j_first + 1 < p.n_peers;
+      __nv_bfloat16* drow = nullptr;
+      if (direct) {
+        const int rg = r0 + row;
+        if (rg < p.Lq) {
+          const int j = rg / p.chunk;
+          drow = p.o_peer_ptr[j] + ((static_cast<size_t>(batch) * p.chunk + (rg - j * p.chunk)) * p.o_heads +
+                                    p.o_head_off + head) * kHeadDim;
+        }
+      }
       const float* bias = nullptr;
       if constexpr (kKeyMod) {
         if (p.out_bias != nullptr && l_tot > 0.f) bias = p.out_bias + head * kHeadDim;
@@ -632,30 +649,44 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           }
           ob[i] = pack_bf16x2(a, b);
         }
-        // 32 columns = 4 x 16-byte chunks of panel (c/2); SWIZZLE_128B: chunk ^= row % 8
-        uint8_t* prow = so + (c >> 1) * kHalfTile + row * 128;
+        if (direct) {
+          if (drow != nullptr) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(ob[4 * q4], ob[4 * q4 + 1], ob[4 * q4 + 2], ob[4 * q4 + 3]);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              *reinterpret_cast<uint4*>(drow + c * 32 + q4 * 8) =
+                  make_uint4(ob[4 * q4], ob[4 * q4 + 1], ob[4 * q4 + 2], ob[4 * q4 + 3]);
+            }
+          }
+        } else {
+          // 32 columns = 4 x 16-byte chunks of panel (c/2); SWIZZLE_128B: chunk ^= row % 8
+          uint8_t* prow = so + (c >> 1) * kHalfTile + row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (c & 1) * 4 + q4;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(ob[4 * q4], ob[4 * q4 + 1], ob[4 * q4 + 2], ob[4 * q4 + 3]);
+          }
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(1 + t, kBlockM);
       if (wq == 0 && lane == 0) {
-        const int r0 = q_row0 + t * kBlockM;
-        if (p.n_peers == 0) {
+        if (r0 >= p.Lq) {
+          // the second tile of the last query block may lie entirely past Lq: nothing to store
+        } else if (p.n_peers == 0) {
           tma_store_4d(&p.tm_o, so, 0, r0, head, batch);
           tma_store_4d(&p.tm_o, so + kHalfTile, 64, r0, head, batch);
-        } else {
-          // the tile may straddle two (or more) ranks' token chunks: one clipped store per rank (rows
-          // outside [0, chunk) of a rank's map are out of bounds and dropped by the TMA unit)
-          const int j_last = min((r0 + kBlockM - 1) / p.chunk, p.n_peers - 1);
-          for (int j = r0 / p.chunk; j <= j_last; ++j) {
-            tma_store_4d(&p.tm_o_peer[j], so, 0, r0 - j * p.chunk, p.o_head_off + head, batch);
-            tma_store_4d(&p.tm_o_peer[j], so + kHalfTile, 64, r0 - j * p.chunk, p.o_head_off + head, batch);
+        } else if (!direct) {
+          // static indices only: the descriptor address must stay a plain param-space address (a
+          // dynamically indexed copy would live in local memory, which TMA cannot read).  Rows past the
+          // end of the last rank's chunk (Lq not a multiple of 128) are out of bounds and dropped.
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j == j_first) {
+              tma_store_4d(&p.tm_o_peer[j], so, 0, r0 - j * p.chunk, p.o_head_off + head, batch);
+              tma_store_4d(&p.tm_o_peer[j], so + kHalfTile, 64, r0 - j * p.chunk, p.o_head_off + head, batch);
+            }
           }
         }
         tma_store_commit();
