@@ -404,6 +404,112 @@ def run_native_arm(args, cfg_key):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: Temperature Modality Alignment cross-attention sweep
+# ------------------------------------------------------------------------------------------------------
+def run_tma_sweep(args):
+    """512 text tokens x {32 760, 75 600} video tokens across the 50-step flow schedule (2 DiT calls per step
+    with classifier-free guidance -> call index c = 0..99, weight w(c) from univid_b200.tma).  Per call: the
+    text-weighted k-norm prologue on the 512 context rows + the fused cross-attention kernel (per-key
+    post-softmax weight, value bias) -- `kernel` -- and the public WanCrossAttention.forward(text_weight=,
+    text_len=) with its q/k/v/o linears -- `module`.  Under torchrun every rank takes L/p query rows (no
+    communication: the context is replicated)."""
+    import torch.distributed as dist
+    from univid_b200 import _ext, tma
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    bf = torch.bfloat16
+    tcfg = tma.TextWeightConfig()
+    calls = 2 * tcfg.total_sampling_steps
+    weights = [tma.calculate_text_weight(c, tcfg) for c in range(calls)]
+    res = {}
+    for key in ("1.3B", "14B"):
+        cfg = CONFIGS[key]
+        dim, heads, text_len = cfg["dim"], cfg["heads"], cfg["text_len"]
+        f, h, w_ = cfg["grid"]
+        L = f * h * w_
+        s = L // world
+        torch.manual_seed(0)
+        ca = mdl.WanCrossAttention(dim, heads).to(dev).eval()
+        for lin in (ca.q, ca.k, ca.v, ca.o):
+            torch.nn.init.xavier_uniform_(lin.weight)
+            torch.nn.init.normal_(lin.bias, std=0.02)
+        x = torch.randn(1, s, dim, device=dev).to(bf)
+        ctx = torch.randn(1, text_len, dim, device=dev).to(bf)
+        tl = tma.text_len_for(ctx, tcfg)
+        with torch.no_grad(), torch.autocast("cuda", dtype=bf):
+            q, _ = ca._prologue(ca.q(x), None, None, None)
+            zero = ctx.new_zeros(1, 1, dim)
+            b_k, b_v = ca.k(zero).flatten().float(), ca.v(zero).flatten().float()
+            k_lin = (ca.k(ctx).float() - b_k).to(bf).contiguous()
+            v_lin = (ca.v(ctx).float() - b_v).to(bf).view(1, text_len, heads, 128)
+            wk = ca.norm_k.weight.float()
+            w_vecs = []
+            for wt in sorted(set(weights)):
+                v_ = torch.ones(text_len, dtype=torch.float32, device=dev)
+                v_[:tl] = wt
+                w_vecs.append((wt, v_))
+            w_of = dict(w_vecs)
+            out = torch.empty(1, s, heads, 128, dtype=bf, device=dev)
+
+            def kernel_call(c):
+                wv = w_of[weights[c]]
+                _, k = _ext.qk_norm_rope(None, k_lin, None, wk, 1e-6, heads, row_scale=wv, pre_bias=b_k)
+                _ext.fmha_fwd(q, k, v_lin, out=out, key_pv_weight=wv, out_bias=b_v)
+
+            def module_call(c):
+                ca(x, ctx, None, text_weight=weights[c], text_len=tl)
+
+            timing = {}
+            for name, fn in (("kernel", kernel_call), ("module", module_call)):
+                for c in range(3):
+                    fn(c)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for c in range(calls):
+                    fn(c)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / calls
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                timing[name] = ms
+        flop = 4.0 * L * text_len * heads * 128
+        bytes_x = 4.0 * L * dim + 4.0 * text_len * dim
+        res[key] = {"video_tokens": L, "heads": heads, "text_len_weighted": tl, "calls": calls,
+                    "kernel_ms_per_call": timing["kernel"], "module_ms_per_call": timing["module"],
+                    "kernel_tflops": flop / (timing["kernel"] * 1e-3) * 1e-12,
+                    "kernel_qo_stream_gbs": bytes_x / (timing["kernel"] * 1e-3) * 1e-9,
+                    "module_tflops_attn_only": flop / (timing["module"] * 1e-3) * 1e-12}
+        del ca, x, q, out
+        torch.cuda.empty_cache()
+    if rank == 0:
+        peaks = load_peaks()
+        line = {"metric": "tma_cross_attention_sweep_tflops", "value": res["1.3B"]["kernel_tflops"], "unit": "TFLOP/s",
+                "n_gpus": world, "steps": calls, "warmup": 3, "ms_per_step": res["1.3B"]["kernel_ms_per_call"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "Temperature Modality Alignment cross-attention sweep: 512 text tokens x "
+                                       "{32760, 75600} video tokens, 50 flow steps x 2 CFG calls, cosine 1.3 -> 1.0",
+                           "weights_first_last": [weights[0], weights[-1]], "transition_calls": int(50 * 0.4)},
+                "sweep": res, "peak_tflops_burst": peaks["tflops_burst"], "hbm_gbs": peaks["hbm_gbs"],
+                "gpu_launches": 2 * calls * 2}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,6 +517,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default=None, choices=list(CONFIGS))
+    ap.add_argument("--workload", default="attention", choices=["attention", "tma-sweep"],
+                    help="attention = the denoise-step attention stack (default, BASELINE configs[1..3]); "
+                         "tma-sweep = the text-weighted cross-attention sweep (configs[4])")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--skip-denoise", action="store_true", help="omit the full WanModel denoise-step timing")
     args = ap.parse_args()
@@ -419,6 +528,8 @@ def main():
     cfg_key = args.config or ("14B" if args.gpus == 8 else "1.3B")
     if args.impl == "reference":
         run_reference_arm(args, cfg_key)
+    elif args.workload == "tma-sweep":
+        run_tma_sweep(args)
     else:
         run_native_arm(args, cfg_key)
 

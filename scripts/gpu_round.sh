@@ -9,6 +9,8 @@ echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_$TAG.err | tee gpurun_out/bench_$TAG.json
 tail -5 gpurun_out/bench_$TAG.err
 echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref_$TAG.json
+echo "== bench tma-sweep" ; timeout 600 python bench.py --workload tma-sweep 2>gpurun_out/bench_sweep_$TAG.err | tee gpurun_out/bench_sweep_$TAG.json
+tail -3 gpurun_out/bench_sweep_$TAG.err
 echo "== kernel battery (prologue + cross)"
 T=univid_b200/csrc/tests/uvb_test
 for c in "prol 1 1950 12 1 0 0" "prol 2 300 12 1 1 0" "prol 1 1000 40 1 0 0" "prol 1 500 24 1 0 0" "prol 1 500 10 1 0 0" \

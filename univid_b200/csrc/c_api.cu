@@ -93,8 +93,7 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const 
 
 unsigned long long* g_timeline = nullptr;   // diagnostics: see uvb_debug_fmha_timeline
 
-constexpr int kFmhaStages = 4;
-constexpr int kFmhaPolyDefault = 0;
+constexpr int kShortKeyTiles = 16;   // <= 2048 keys: query-block-pipelined variant
 constexpr size_t kWsFlagBytes = 4096;   // flags [sms][2] u32 live at the start of the workspace
 
 int sm_count(int* out) {
@@ -167,12 +166,7 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timeline = g_timeline;
 
-  // Tuning hooks (read once): UVB_FMHA_POLY=0|2|4 share of the exp2 evaluated on the FMA pipe (one pair in
-  // every N); UVB_FMHA_SPLIT=0 disables the split of the remainder units across CTAs.
-  static const int poly = [] {
-    const char* e = getenv("UVB_FMHA_POLY");
-    return e != nullptr ? atoi(e) : kFmhaPolyDefault;
-  }();
+  // Tuning hook (read once): UVB_FMHA_SPLIT=0 disables the split of the remainder units across CTAs.
   static const bool allow_split = [] {
     const char* e = getenv("UVB_FMHA_SPLIT");
     return e == nullptr || atoi(e) != 0;
@@ -193,10 +187,12 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     grid_x = iters < sms ? iters : sms;
   }
 
-  void (*kern)(uvb::FmhaParams) = poly == 2 ? uvb::fmha_fwd_kernel<kFmhaStages, 2, kKeyMod>
-                                : poly == 4 ? uvb::fmha_fwd_kernel<kFmhaStages, 4, kKeyMod>
-                                            : uvb::fmha_fwd_kernel<kFmhaStages, 0, kKeyMod>;
-  constexpr int smem = uvb::FmhaSmem<kFmhaStages>::kDynBytes;
+  // Few key tiles per query block (cross-attention: 4): the per-block prologue/epilogue dominates, so use
+  // the variant that prefetches the next block's Q and drains O through a second buffer (3 ring slots);
+  // long key sequences keep the deeper K/V ring instead.
+  const bool short_keys = n_kv <= kShortKeyTiles;
+  void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 0, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 0, kKeyMod>;
+  const int smem = short_keys ? uvb::FmhaSmem<3, 2>::kDynBytes : uvb::FmhaSmem<4, 1>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<dim3(static_cast<unsigned>(grid_x)), uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   UVB_CUDA(cudaGetLastError());

@@ -53,13 +53,16 @@ constexpr float kRescaleThreshold = 8.0f;            // lazy rescale: only when 
 constexpr int kWsOFloats = kHeadDim * kUnitRows;
 constexpr int kWsSlotFloats = kWsOFloats + 2 * kUnitRows;
 
-template <int kStages>
+// kStages K/V ring slots, kQBufs query-block buffers.  Self-attention (hundreds of key tiles per query
+// block) uses <4, 1>; cross-attention (4 key tiles per query block) uses <3, 2>: the next block's Q is
+// prefetched while the current one is computed and its O tile drains through the other buffer.
+template <int kStages, int kQBufs>
 struct FmhaSmem {
   static constexpr int kQOff = 0;
-  static constexpr int kKvOff = kQTiles * kTileBytes;
+  static constexpr int kKvOff = kQBufs * kQTiles * kTileBytes;
   static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
-  // barriers: q_full[2] q_empty[2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
-  static constexpr int kNumBars = 4 + 2 * kStages + 10;
+  // barriers: q_full[B][2] q_empty[B][2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
+  static constexpr int kNumBars = 4 * kQBufs + 2 * kStages + 10;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for 1024 B alignment
 };
@@ -181,10 +184,11 @@ __device__ __forceinline__ void softmax_exp64(const uint32_t* sr, float scale_lo
   }
 }
 
-template <int kStages, int kPolyEvery, bool kKeyMod>
+template <int kStages, int kQBufs, int kPolyEvery, bool kKeyMod>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
-  using SM = FmhaSmem<kStages>;
+  using SM = FmhaSmem<kStages, kQBufs>;
+  static_assert(SM::kDynBytes <= 232448, "shared memory budget (227 KiB)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -194,9 +198,9 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   uint8_t* smem_q = smem + SM::kQOff;
   uint8_t* smem_kv = smem + SM::kKvOff;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
-  uint64_t* q_full = bars;                       // [tile]   TMA -> MMA: Q_t of the segment landed
-  uint64_t* q_empty = bars + 2;                  // [tile]   softmax -> TMA: Q_t / O staging is free again
-  uint64_t* kv_full = bars + 4;                  // [kStages]
+  uint64_t* q_full = bars;                       // [buf][tile]  TMA -> MMA: Q_t of the segment landed
+  uint64_t* q_empty = bars + 2 * kQBufs;         // [buf][tile]  softmax -> TMA: Q_t / O staging is free again
+  uint64_t* kv_full = bars + 4 * kQBufs;         // [kStages]
   uint64_t* kv_empty = kv_full + kStages;        // [kStages]
   uint64_t* s_full = kv_empty + kStages;         // [tile]
   uint64_t* p_full = s_full + 2;                 // [tile][half]
@@ -208,9 +212,11 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kQBufs; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&q_full[t], 1);
-      mbar_init(&q_empty[t], 1);
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[2 * t], 4);       // one arrive per softmax warp
       mbar_init(&p_full[2 * t + 1], 4);
@@ -267,14 +273,16 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         const FmhaSeg sg = sch.seg(si);
         int batch, head, q_row0, k_len, ka, kb;
         decode(sg, batch, head, q_row0, k_len, ka, kb);
+        const int qb = si % kQBufs;                      // query-block buffer of this segment
+        const uint32_t qpar = (si / kQBufs) & 1;
         for (int t = 0; t < kQTiles; ++t) {
-          mbar_wait(&q_empty[t], (si & 1) ^ 1);
-          uint8_t* dst = smem_q + t * kTileBytes;
+          uint64_t* full = &q_full[2 * qb + t];
+          mbar_wait(&q_empty[2 * qb + t], qpar ^ 1);
+          uint8_t* dst = smem_q + (2 * qb + t) * kTileBytes;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&q_full[t], kTileBytes);
-            tma_load_4d_hint(dst, &p.tm_q, &q_full[t], 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
-            tma_load_4d_hint(dst + kHalfTile, &p.tm_q, &q_full[t], 64, q_row0 + t * kBlockM, head, batch,
-                             kEvictFirst);
+            mbar_arrive_expect_tx(full, kTileBytes);
+            tma_load_4d_hint(dst, &p.tm_q, full, 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+            tma_load_4d_hint(dst + kHalfTile, &p.tm_q, full, 64, q_row0 + t * kBlockM, head, batch, kEvictFirst);
           }
           __syncwarp();
         }
@@ -317,8 +325,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       };
       // S_t = Q_t K^T : A, B K-major, N = 128 keys; 8 K-steps of 16 dims: panel = kk/4, 32 B per K-step
       // inside the 128 B swizzle atom
-      auto issue_qk = [&](int t, int k_ring) {
-        const uint64_t qa = q_desc + t * kTile16;
+      auto issue_qk = [&](int qt, int t, int k_ring) {   // qt = 2 * query buffer + tile
+        const uint64_t qa = q_desc + qt * kTile16;
         const uint64_t ka = k_desc + (k_ring % kStages) * kTile16;
         const uint32_t d = tmem_base + t * 128;
         if (elect_one()) {
@@ -354,22 +362,24 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         int batch, head, q_row0, k_len, ka, kb;
         decode(sg, batch, head, q_row0, k_len, ka, kb);
         const int n_steps = kb - ka;
-        mbar_wait(&q_full[0], si & 1);
+        const int qb = si % kQBufs;
+        const uint32_t qpar = (si / kQBufs) & 1;
+        mbar_wait(&q_full[2 * qb], qpar);
         tc_fence_after();
         if (n_steps == 0) {
           // nothing to attend to (k_lens clipped the range away): the epilogue treats O as zero
-          mbar_wait(&q_full[1], si & 1);
+          mbar_wait(&q_full[2 * qb + 1], qpar);
           commit(&o_full[0]);
           commit(&o_full[1]);
           continue;
         }
         // prologue: scores of the first step of both tiles
         wait_full(ring);
-        issue_qk(0, ring);
+        issue_qk(2 * qb, 0, ring);
         commit(&s_full[0]);
-        mbar_wait(&q_full[1], si & 1);
+        mbar_wait(&q_full[2 * qb + 1], qpar);
         tc_fence_after();
-        issue_qk(1, ring);
+        issue_qk(2 * qb + 1, 1, ring);
         commit(&s_full[1]);
         commit(&kv_empty[ring % kStages]);   // K tile of step 0 is fully consumed by the prologue
 
@@ -391,7 +401,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             commit(&pv_done[t]);
             if (more) {
               if (t == 0) wait_full(k_ring);
-              issue_qk(t, k_ring);
+              issue_qk(2 * qb + t, t, k_ring);
               commit(&s_full[t]);
             } else {
               commit(&o_full[t]);
@@ -551,7 +561,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         named_bar_sync(1 + t, kBlockM);
         if (wq == 0 && lane == 0) {
           st_release_gpu(p.flags + 2 * sch.g + t, 1u);
-          mbar_arrive(&q_empty[t]);
+          mbar_arrive(&q_empty[2 * (si % kQBufs) + t]);
         }
         continue;
       }
@@ -589,7 +599,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
       const float own_scale = alpha * inv;
 
-      uint8_t* so = smem_q + t * kTileBytes;  // Q_t is dead once o_full[t] has fired
+      uint8_t* so = smem_q + (2 * (si % kQBufs) + t) * kTileBytes;  // Q_t is dead once o_full[t] has fired
       // Peer mode: a tile whose 128 rows lie in ONE rank's token chunk is TMA-stored into that rank's
       // buffer; a tile that straddles chunks is written row by row with plain stores (each thread owns a
       // row and picks its rank) -- TMA rejects the negative start coordinate a clipped store would need.
@@ -696,7 +706,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           }
         }
         tma_store_wait_read0();          // the staging buffer may be overwritten by the next Q_t
-        mbar_arrive(&q_empty[t]);
+        mbar_arrive(&q_empty[2 * (si % kQBufs) + t]);
         stored = true;
       }
     }
