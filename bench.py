@@ -351,9 +351,12 @@ def run_native_arm(args, cfg_key):
            "api": "WanSelfAttention.forward + WanCrossAttention.forward per layer (q/k/v/o linears included), "
                   "x/context from pinned host memory, result copied back"}
 
-    # ---------------- full denoise step through the WanModel harness (once; N = 1 only) ---------------
+    # ---------------- full denoise step through the WanModel harness ------------------------------------
+    # N > 1: sp_attn_forward / sp_dit_forward are bound onto the instance exactly like the reference does
+    # with use_sp=True (textimage2video.py:143-147): tokens sharded over the ranks, Ulysses around attention.
     denoise_ms = None
-    if world == 1 and not args.skip_denoise:
+    if not args.skip_denoise:
+        import types
         del sets
         torch.cuda.empty_cache()
         torch.manual_seed(0)
@@ -361,19 +364,28 @@ def run_native_arm(args, cfg_key):
             model = mdl.WanModel(model_type="t2v", dim=dim, ffn_dim=cfg["ffn"], num_heads=heads, num_layers=layers,
                                  text_len=text_len, in_dim=16, out_dim=16)
         model = model.eval()
-        lat = [torch.randn(16, f, h * 2, w * 2, device=dev)]
-        ctx = [torch.randn(text_len, 4096, device=dev)]
+        if world > 1:
+            for block in model.blocks:
+                block.self_attn.forward = types.MethodType(sp.sp_attn_forward, block.self_attn)
+            model.forward = types.MethodType(sp.sp_dit_forward, model)
+        gen = torch.Generator(device=dev).manual_seed(7)      # identical inputs on every rank
+        lat = [torch.randn(16, f, h * 2, w * 2, device=dev, generator=gen)]
+        ctx_in = [torch.randn(text_len, 4096, device=dev, generator=gen)]
         tt = torch.tensor([500.0], device=dev)
         with torch.no_grad(), torch.autocast("cuda", dtype=bf):
-            model(lat, tt, ctx, seq_len=L)
-            torch.cuda.synchronize()
+            model(lat, tt, ctx_in, seq_len=L)
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(2):
-                model(lat, tt, ctx, seq_len=L)
+                model(lat, tt, ctx_in, seq_len=L)
             e1.record()
-            torch.cuda.synchronize()
+            barrier()
         denoise_ms = e0.elapsed_time(e1) / 2
+        if world > 1:
+            tms = torch.tensor([denoise_ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            denoise_ms = float(tms.item())
         del model
 
     if rank == 0:
@@ -459,10 +471,13 @@ def run_tma_sweep(args):
             w_of = dict(w_vecs)
             out = torch.empty(1, s, heads, 128, dtype=bf, device=dev)
 
+            v_f32 = v_lin.float()
+
             def kernel_call(c):
                 wv = w_of[weights[c]]
                 _, k = _ext.qk_norm_rope(None, k_lin, None, wk, 1e-6, heads, row_scale=wv, pre_bias=b_k)
-                _ext.fmha_fwd(q, k, v_lin, out=out, key_pv_weight=wv, out_bias=b_v)
+                v_w = (v_f32 * wv.view(1, text_len, 1, 1)).to(bf)       # 512 rows: the weight rides on V
+                _ext.fmha_fwd(q, k, v_w, out=out, out_bias=b_v)
 
             def module_call(c):
                 ca(x, ctx, None, text_weight=weights[c], text_len=tl)

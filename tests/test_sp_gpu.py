@@ -30,7 +30,7 @@ def _worker(rank, world, port, out, transport):
         sp = importlib.import_module("univid_b200.wan.distributed.sequence_parallel")
         uly = importlib.import_module("univid_b200.wan.distributed.ulysses")
         g = torch.Generator().manual_seed(0)
-        dim, heads, L = 512, 4, 4 * 61 * world // world * 1
+        dim, heads = (512, 4) if world <= 4 else (1024, 8)
         L = 240 if world <= 4 else 480
         prm = orc.init_attention_params(dim, g, realistic_bias=True)
         x = torch.randn(1, L, dim, generator=g).to(torch.bfloat16).float()
@@ -64,9 +64,10 @@ def _worker(rank, world, port, out, transport):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sp_attention_equals_unsharded(world, transport):
-    """L = 240 tokens -> 120 / 60 per rank: every 128-row output tile straddles two or three ranks' chunks."""
+    """L = 240 tokens -> 120 / 60 per rank (480 -> 60 at 8 ranks): every 128-row output tile straddles two or
+    three ranks' chunks."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     mgr = mp.Manager()

@@ -204,8 +204,8 @@ class WanCrossAttention(WanSelfAttention):
             text_weight, text_len: opt-in FUSED form of UniVid's dynamic text weighting: equivalent to
                 calling with context[:, :text_len] * text_weight (what Wan22ContextWrapper's hook does,
                 model_pipeline.py:1789-1797) but the scaled context is never materialised: the weight is
-                folded into the k-norm prologue and applied to the probabilities inside the attention
-                kernel.  With the defaults this is the reference forward (model.py:160-180); a context
+                folded into the k-norm prologue (exactly: k' = RMSNorm(w u + b_k)) and into the 512
+                bias-free value rows, with the value bias added to the normalised output by the kernel.  With the defaults this is the reference forward (model.py:160-180); a context
                 pre-scaled by the reference hook goes through that default path unchanged.
         """
         b, n, d = x.size(0), self.num_heads, self.head_dim
@@ -226,16 +226,17 @@ class WanCrossAttention(WanSelfAttention):
         lk = context.size(1)
         zero = context.new_zeros(1, 1, context.size(-1))
         b_k, b_v = self.k(zero).flatten().float(), self.v(zero).flatten().float()
-        k_lin = (self.k(context).float() - b_k).to(torch.bfloat16)
-        v_lin = (self.v(context).float() - b_v).to(torch.bfloat16).view(b, lk, n, d)
         w_vec = torch.ones(lk, dtype=torch.float32, device=x.device)
         w_vec[:text_len] = float(text_weight)
+        k_lin = (self.k(context).float() - b_k).to(torch.bfloat16)
+        # out = sum_j p_j (w_j l_j + b_v) = sum_j p_j (w_j l_j) + b_v: the weight rides on the 512 bias-free
+        # value rows (one tiny elementwise op) instead of on every probability inside the attention kernel
+        v_lin = ((self.v(context).float() - b_v) * w_vec.view(1, lk, 1)).to(torch.bfloat16).view(b, lk, n, d)
         wk, eps_k, pre_k = _norm_weight(self.norm_k)
         if pre_k is not None:
             raise NotImplementedError('fused text weighting needs a WanRMSNorm or Identity norm_k')
         _, k = _ext.qk_norm_rope(None, k_lin.contiguous(), None, wk, eps_k, n, row_scale=w_vec, pre_bias=b_k)
-        x = _ext.fmha_fwd(q, k, v_lin, k_lens=_k_lens_arg(context_lens, b, lk, x.device),
-                          key_pv_weight=w_vec, out_bias=b_v)
+        x = _ext.fmha_fwd(q, k, v_lin, k_lens=_k_lens_arg(context_lens, b, lk, x.device), out_bias=b_v)
         return self._out_proj(x)
 
 
