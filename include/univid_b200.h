@@ -139,6 +139,25 @@ int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* cons
                          const int64_t* v_strides, float scale, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
+/* Fused elementwise glue of a WanAttentionBlock around the attention calls.
+ * Replaces, per call, the eager chain of WanAttentionBlock.forward (model.py:244-257): the gated residual
+ * `x = x + y * e[k]` (:247 / :252 / :257), WanLayerNorm (:88-98: norm1 / norm2 without affine, norm3 with),
+ * the adaLN modulation `norm(x).float() * (1 + e[k]) + e[k']` (:244 / :255) and the autocast cast of the
+ * result to bf16 at the consuming nn.Linear.
+ *
+ *   x' = x_in + y * gate        if y != NULL (y bf16 [B, L, dim]; gate NULL = 1); x' is stored to x_out
+ *                               (fp32, may alias x_in)
+ *   h  = LayerNorm(x') * ln_w + ln_b  (ln_w / ln_b NULL = no affine), eps inside the rsqrt
+ *   h  = h * (1 + scale) + shift      (both NULL = no modulation)   -> h_out bf16 [B, L, dim]; h_out NULL
+ *                               skips the LayerNorm part (residual update only)
+ *   gate / scale / shift are fp32 views into the modulation tensor (modulation + e).chunk(6): element
+ *   (b, l, c) at ptr + b*mod_sb + l*mod_sl + c (element strides; mod_sl = 0 broadcasts one row per sample).
+ *   dim in {256, 512, 1024, 1536, 2048, 3072, 4096, 5120}; all pointers 16-byte aligned.
+ */
+int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x_out, const float* ln_w,
+                   const float* ln_b, const float* scale, const float* shift, void* h_out, int B, int L,
+                   int dim, int64_t mod_sb, int64_t mod_sl, float eps, void* stream);
+
 /* Diagnostics: when set to a DEVICE buffer of (number of SMs) x 32 uint64, every attention launch records
  * per CTA {smid, start ns, end ns of each piece of work (up to 30)} (%globaltimer).  NULL (default) = off. */
 void uvb_debug_fmha_timeline(void* device_buffer);

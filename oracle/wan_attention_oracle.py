@@ -226,6 +226,54 @@ def cross_attention(x, context, prm, num_heads, context_lens=None, eps=1e-6, bf1
 
 
 # ------------------------------------------------------------------------------------------------
+# WanLayerNorm -- model.py:88-98 ; WanAttentionBlock -- model.py:183-259
+# ------------------------------------------------------------------------------------------------
+def layer_norm(x, eps, weight=None, bias=None):
+    """nn.LayerNorm.forward(x.float()).type_as(x) (model.py:92-98): statistics and affine in fp32, result
+    rounded back to x's dtype."""
+    return F.layer_norm(x.float(), (x.shape[-1],), None if weight is None else weight.float(),
+                        None if bias is None else bias.float(), eps).to(x.dtype)
+
+
+def attention_block(x, e, prm, seq_lens, grid_sizes, freqs, context, context_lens, num_heads, eps=1e-6,
+                    bf16=True, route="sdpa", cross_attn_norm=True):
+    """WanAttentionBlock.forward (model.py:219-259).  prm holds the block's state dict ('modulation',
+    'self_attn.*', 'norm3.*', 'cross_attn.*', 'ffn.0.*', 'ffn.2.*').  e: fp32 [B, L1, 6, C].
+    Dtype flow under bf16 autocast: the modulation arithmetic and the residual updates run in fp32
+    (:239-240, :246-247, :256-257), every nn.Linear rounds its input to bf16 and returns bf16, GELU(tanh)
+    acts on the bf16 output of ffn.0."""
+    assert e.dtype == torch.float32
+    sub = lambda pre: {k[len(pre):]: v for k, v in prm.items() if k.startswith(pre)}
+    m = (prm["modulation"].float().unsqueeze(0) + e).chunk(6, dim=2)                     # :239
+    m = [u.squeeze(2) for u in m]
+    h = layer_norm(x, eps).float() * (1 + m[1]) + m[0]                                    # :244
+    y = self_attention(h, sub("self_attn."), seq_lens, grid_sizes, freqs, num_heads, eps, bf16, route)
+    x = x + y * m[2]                                                                       # :247
+    n3 = layer_norm(x, eps, prm["norm3.weight"], prm["norm3.bias"]) if cross_attn_norm else x
+    x = x + cross_attention(n3, context, sub("cross_attn."), num_heads, context_lens, eps, bf16, route)   # :252
+    h = layer_norm(x, eps).float() * (1 + m[4]) + m[3]                                    # :254-255
+    f = _linear(h, prm["ffn.0.weight"], prm["ffn.0.bias"], bf16)
+    f = F.gelu(f, approximate="tanh")
+    y = _linear(f, prm["ffn.2.weight"], prm["ffn.2.bias"], bf16)
+    return x + y * m[5]                                                                    # :257
+
+
+def init_block_params(dim, ffn_dim, generator, realistic_bias=True):
+    """State dict of one WanAttentionBlock (cross_attn_norm=True) with the init rules of SURVEY.md sec. 8d."""
+    prm = {"modulation": torch.randn(1, 6, dim, generator=generator) / dim ** 0.5}
+    for pre in ("self_attn.", "cross_attn."):
+        for k, v in init_attention_params(dim, generator, realistic_bias).items():
+            prm[pre + k] = v
+    prm["norm3.weight"] = 1 + 0.1 * torch.randn(dim, generator=generator)
+    prm["norm3.bias"] = 0.05 * torch.randn(dim, generator=generator)
+    for name, (o, i) in (("ffn.0", (ffn_dim, dim)), ("ffn.2", (dim, ffn_dim))):
+        bound = math.sqrt(6.0 / (o + i))
+        prm[f"{name}.weight"] = (torch.rand(o, i, generator=generator) * 2 - 1) * bound
+        prm[f"{name}.bias"] = torch.randn(o, generator=generator) * 0.02
+    return prm
+
+
+# ------------------------------------------------------------------------------------------------
 # Temperature Modality Alignment -- model_pipeline.py:1699-1735 (schedule), :1756-1803 (hook)
 # ------------------------------------------------------------------------------------------------
 def text_weight(call_index, total_sampling_steps=50, transition_ratio=0.4, w_max=1.3, w_min=1.0,

@@ -1,0 +1,77 @@
+"""WanAttentionBlock on the GPU: the fused glue kernel (uvb_block_glue) against its fp32 torch expression, and
+the whole block (fused glue + attention kernels) against the oracle pinned to the reference block.  -m gpu."""
+import importlib
+import os
+
+import pytest
+import torch
+
+from oracle import wan_attention_oracle as orc
+from tests.golden.make_block_golden import DIM, EPS, FFN, HEADS, block_case
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("dim", [256, 512, 1024, 1536, 2048, 3072, 4096, 5120])
+@pytest.mark.parametrize("per_tok", [False, True])
+def test_block_glue_kernel(dim, per_tok):
+    from univid_b200 import _ext
+    g = torch.Generator().manual_seed(dim + per_tok)
+    B, L = 2, 37
+    x = torch.randn(B, L, dim, generator=g).cuda() * 3 + 0.5
+    y = torch.randn(B, L, dim, generator=g).to(torch.bfloat16).cuda()
+    mod = (0.3 * torch.randn(B, L if per_tok else 1, 6, dim, generator=g)).cuda()
+    w, b = (1 + 0.1 * torch.randn(dim, generator=g)).cuda(), (0.1 * torch.randn(dim, generator=g)).cuda()
+    shift, scale, gate = mod[:, :, 0], mod[:, :, 1], mod[:, :, 2]
+    ln = lambda t, ww=None, bb=None: torch.nn.functional.layer_norm(t, (dim,), ww, bb, 1e-6)
+    # LN + modulation only
+    _, h = _ext.block_glue(x, scale=scale, shift=shift, eps=1e-6)
+    want = torch.addcmul(shift, ln(x), 1 + scale)
+    assert h.dtype == torch.bfloat16 and (h.float() - want).abs().max() <= 0.0079 * want.abs().max()
+    assert (h == want.to(torch.bfloat16)).float().mean() > 0.99          # same rounding point, rare 1-ulp flips
+    # gated residual + affine LN, out of place
+    x0 = x.clone()
+    x1, h = _ext.block_glue(x, y=y, gate=gate, ln=(w, b), eps=1e-6)
+    want_x = x0 + y.float() * gate
+    assert torch.equal(x, x0) and torch.equal(x1, want_x)
+    assert (h == ln(want_x, w, b).to(torch.bfloat16)).float().mean() > 0.99
+    # plain residual, modulated LN, in place
+    x2, h = _ext.block_glue(x1, y=y, gate=None, scale=scale, shift=shift, eps=1e-6, inplace=True)
+    want_x2 = want_x + y.float()
+    assert x2.data_ptr() == x1.data_ptr() and torch.equal(x2, want_x2)
+    assert (h == torch.addcmul(shift, ln(want_x2), 1 + scale).to(torch.bfloat16)).float().mean() > 0.99
+    # residual only
+    x3, none = _ext.block_glue(x2, y=y, gate=gate, want_h=False, inplace=True)
+    assert none is None and torch.equal(x3, want_x2 + y.float() * gate)
+
+
+@pytest.mark.parametrize("per_tok", [False, True])
+def test_block_matches_oracle(per_tok):
+    """Fused block vs the oracle (bit-exactly pinned to the reference block by tests/test_block_oracle_golden.py):
+    north-star tolerance against the fp32 evaluation, and the eager-glue path of the same module as a cross-check."""
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    case = block_case(3, per_tok)
+    freqs = orc.make_freqs(128)
+    want32 = orc.attention_block(case["x"], case["e"], case["prm"], case["seq_lens"], case["grid_sizes"], freqs,
+                                 case["context"], None, HEADS, eps=EPS, bf16=False)
+    blk = mdl.WanAttentionBlock(DIM, FFN, HEADS, cross_attn_norm=True, eps=EPS)
+    blk.load_state_dict(case["prm"])
+    blk = blk.cuda().eval()
+    args = (case["x"].cuda(), case["e"].cuda(), case["seq_lens"], case["grid_sizes"], freqs.cuda(), case["context"].cuda(), None)
+    x_before = args[0].clone()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert blk._fused_glue_ok(args[0], args[1])
+        got = blk(*args)
+        blk._fused_glue_ok = lambda *a: False          # eager glue, same attention kernels
+        eager = blk(*args)
+    assert torch.equal(args[0], x_before), "the block must not modify its input"
+    assert got.dtype == torch.float32
+    err = (got.cpu() - want32).abs().max().item()
+    assert err <= 2e-2 and _cos(got.cpu(), want32) >= 0.9999, (err, _cos(got.cpu(), want32))
+    assert (got - eager).abs().max().item() <= 2e-2

@@ -8,6 +8,7 @@
 #include "../../include/univid_b200.h"
 #include "fmha_fwd_sm100.cuh"
 #include "qk_norm_rope.cuh"
+#include "block_glue.cuh"
 
 namespace {
 
@@ -229,7 +230,7 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 102; }
+int uvb_version(void) { return 103; }
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -365,6 +366,63 @@ int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, cons
                       float scale, void* workspace, int64_t workspace_bytes, void* stream) {
   return launch_fmha<false>(q, k, v, o, k_lens, nullptr, nullptr, nullptr, B, Lq, Lk, N, q_strides,
                             k_strides, v_strides, o_strides, scale, workspace, workspace_bytes, stream);
+}
+
+int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x_out, const float* ln_w,
+                   const float* ln_b, const float* scale, const float* shift, void* h_out, int B, int L,
+                   int dim, int64_t mod_sb, int64_t mod_sl, float eps, void* stream) {
+  if (x_in == nullptr) return fail(UVB_ERR_INVALID, "x_in is null");
+  if (B <= 0 || L <= 0 || dim <= 0) return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d dim=%d", B, L, dim);
+  if (y == nullptr && h_out == nullptr) return fail(UVB_ERR_INVALID, "nothing to do (y and h_out are both null)");
+  if (y != nullptr && x_out == nullptr) return fail(UVB_ERR_INVALID, "x_out is required with y");
+  if (y == nullptr && gate != nullptr) return fail(UVB_ERR_INVALID, "gate without y");
+  if ((scale == nullptr) != (shift == nullptr)) return fail(UVB_ERR_INVALID, "scale and shift go together");
+  if (mod_sb % 4 != 0 || mod_sl % 4 != 0) return fail(UVB_ERR_INVALID, "modulation strides must be multiples of 4");
+  for (const void* q : {static_cast<const void*>(x_in), y, static_cast<const void*>(gate),
+                        static_cast<const void*>(x_out), static_cast<const void*>(ln_w),
+                        static_cast<const void*>(ln_b), static_cast<const void*>(scale),
+                        static_cast<const void*>(shift), static_cast<const void*>(h_out)}) {
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return fail(UVB_ERR_INVALID, "pointers must be 16-byte aligned");
+  }
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+  uvb::BlockGlueParams p;
+  memset(&p, 0, sizeof(p));
+  p.x_in = x_in;
+  p.y = static_cast<const __nv_bfloat16*>(y);
+  p.gate = gate;
+  p.x_out = x_out;
+  p.ln_w = ln_w;
+  p.ln_b = ln_b;
+  p.scale = scale;
+  p.shift = shift;
+  p.h_out = static_cast<__nv_bfloat16*>(h_out);
+  p.rows = static_cast<long long>(B) * L;
+  p.L = L;
+  p.dim = dim;
+  p.mod_sb = mod_sb;
+  p.mod_sl = mod_sl;
+  p.eps = eps;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 block(uvb::kGlueWarps * 32);
+  auto blocks = [&](int wpr) {
+    const long long per_cta = uvb::kGlueWarps / wpr;
+    return static_cast<unsigned>((p.rows + per_cta - 1) / per_cta);
+  };
+  switch (dim) {   // 256 * VPL * WPR
+    case 256: uvb::block_glue_kernel<1, 1><<<blocks(1), block, 0, st>>>(p); break;
+    case 512: uvb::block_glue_kernel<2, 1><<<blocks(1), block, 0, st>>>(p); break;
+    case 1024: uvb::block_glue_kernel<4, 1><<<blocks(1), block, 0, st>>>(p); break;
+    case 1536: uvb::block_glue_kernel<3, 2><<<blocks(2), block, 0, st>>>(p); break;
+    case 2048: uvb::block_glue_kernel<4, 2><<<blocks(2), block, 0, st>>>(p); break;
+    case 3072: uvb::block_glue_kernel<3, 4><<<blocks(4), block, 0, st>>>(p); break;
+    case 4096: uvb::block_glue_kernel<4, 4><<<blocks(4), block, 0, st>>>(p); break;
+    case 5120: uvb::block_glue_kernel<5, 4><<<blocks(4), block, 0, st>>>(p); break;
+    default:
+      return fail(UVB_ERR_UNSUPPORTED, "block glue supports dim in {256, 512, 1024, 1536, 2048, 3072, 4096, 5120}, got %d", dim);
+  }
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
 }
 
 int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,

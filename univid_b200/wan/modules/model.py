@@ -275,8 +275,12 @@ class WanAttentionBlock(nn.Module):
         """
         assert e.dtype == torch.float32
         with torch.amp.autocast('cuda', dtype=torch.float32):
-            shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = (
-                u.squeeze(2) for u in (self.modulation.unsqueeze(0) + e).chunk(6, dim=2))
+            mod = self.modulation.unsqueeze(0) + e                       # fp32 [B, L or 1, 6, C]
+        shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = (mod[:, :, k] for k in range(6))
+
+        if self._fused_glue_ok(x, mod):
+            return self._forward_fused(x, (shift_a, scale_a, gate_a, shift_f, scale_f, gate_f), seq_lens, grid_sizes,
+                                       freqs, context, context_lens)
 
         y = self.self_attn(torch.addcmul(shift_a, self.norm1(x).float(), 1 + scale_a), seq_lens, grid_sizes, freqs)
         with torch.amp.autocast('cuda', dtype=torch.float32):
@@ -286,6 +290,39 @@ class WanAttentionBlock(nn.Module):
         with torch.amp.autocast('cuda', dtype=torch.float32):
             x = x + y * gate_f
         return x
+
+    def _fused_glue_ok(self, x, mod):
+        """The fused glue kernel covers the inference configuration of the product: fp32 residual stream on the
+        GPU, bf16 autocast (so the branch outputs are bf16), no autograd, plain WanLayerNorm / Identity norms."""
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.size(-1) in _ext.GLUE_DIMS
+                and torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
+                and not (torch.is_grad_enabled() and (x.requires_grad or mod.requires_grad))
+                and type(self.norm1) is WanLayerNorm and type(self.norm2) is WanLayerNorm
+                and type(self.norm3) in (WanLayerNorm, nn.Identity)
+                and not self.norm1.elementwise_affine and not self.norm2.elementwise_affine)
+
+    def _forward_fused(self, x, mods, seq_lens, grid_sizes, freqs, context, context_lens):
+        """Same dataflow as above with the elementwise glue in uvb_block_glue: one pass per residual update,
+        producing the next branch's bf16 input in the same pass."""
+        shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = mods
+        x = x.contiguous()
+        _, h = _ext.block_glue(x, scale=scale_a, shift=shift_a, eps=self.norm1.eps)
+        y = self.self_attn(h, seq_lens, grid_sizes, freqs)
+        if isinstance(self.norm3, WanLayerNorm):
+            ln3 = (self.norm3.weight, self.norm3.bias) if self.norm3.elementwise_affine else (None, None)
+            x, h = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, ln=ln3, eps=self.norm3.eps)     # new x: the caller's is kept
+        else:
+            x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, want_h=False)
+            h = x
+        c = self.cross_attn(h, context, context_lens)
+        x, h = _ext.block_glue(x, y=_bf16c(c), gate=None, scale=scale_f, shift=shift_f, eps=self.norm2.eps, inplace=True)
+        y = self.ffn(h)
+        x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_f, want_h=False, inplace=True)
+        return x
+
+
+def _bf16c(t):
+    return (t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)).contiguous()
 
 
 class Head(nn.Module):
