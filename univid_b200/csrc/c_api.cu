@@ -192,7 +192,15 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   // the variant that prefetches the next block's Q and drains O through a second buffer (3 ring slots);
   // long key sequences keep the deeper K/V ring instead.
   const bool short_keys = n_kv <= kShortKeyTiles;
+  // UVB_FMHA_POLY=N (experiment hook): one exp2 pair in every N goes through the FMA-pipe polynomial
+  static const int poly = [] {
+    const char* e = getenv("UVB_FMHA_POLY");
+    return e != nullptr ? atoi(e) : 0;
+  }();
   void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 0, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 0, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 4) kern = uvb::fmha_fwd_kernel<4, 1, 4, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 8) kern = uvb::fmha_fwd_kernel<4, 1, 8, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 3) kern = uvb::fmha_fwd_kernel<4, 1, 3, kKeyMod>;
   const int smem = short_keys ? uvb::FmhaSmem<3, 2>::kDynBytes : uvb::FmhaSmem<4, 1>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<dim3(static_cast<unsigned>(grid_x)), uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
