@@ -232,3 +232,23 @@ def test_sp_kernels_with_local_peers(ext, p, s, heads, batch):
     got = torch.cat(o_recv, dim=1)                                   # [B, L, N, 128]
     assert torch.isfinite(got.float()).all(), "an output row was not written"
     assert torch.equal(got, o_ref)
+
+
+@pytest.mark.parametrize("b,lq,lk,n,lens", [(1, 1950, 1950, 12, None), (2, 700, 2300, 3, [2300, 130]), (1, 40000, 512, 5, None),
+                                             (1, 9000, 4000, 20, None), (3, 300, 300, 2, [0, 300, 17])])
+def test_fmha_split_and_unsplit_schedules_agree(ext, b, lq, lk, n, lens):
+    """The persistent kernel with the stream-K split of remainder query blocks (workspace) against the schedule
+    that never splits (workspace = NULL), and both against the oracle on sampled rows.  Repeated launches reuse
+    the workspace flags (they must come back zeroed)."""
+    g = torch.Generator().manual_seed(lq + lk)
+    q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16).cuda() for l in (lq, lk, lk))
+    kl = None if lens is None else torch.tensor(lens, dtype=torch.int32, device="cuda")
+    ref = ext.fmha_fwd(q, k, v, k_lens=kl, split_units=False)
+    for _ in range(3):
+        got = ext.fmha_fwd(q, k, v, k_lens=kl)
+        assert torch.isfinite(got.float()).all()
+        assert (got.float() - ref.float()).abs().max().item() <= 4e-3      # same math, different merge order
+    rows = torch.randperm(lq, generator=g)[:64]
+    want = orc.attention_varlen(q[:, rows].float().cpu(), k.float().cpu(), v.float().cpu(),
+                                k_lens=None if lens is None else torch.tensor(lens), compute_dtype=torch.float32)
+    _check_attn(got[:, rows], want)

@@ -273,7 +273,7 @@ def _fmha_workspace(device, stream):
 
 
 def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale=None,
-             key_pv_weight=None, out_bias=None):
+             key_pv_weight=None, out_bias=None, split_units=True):
     """softmax(q k^T * scale) v on [B, L, N, 128] bf16 tensors (any strides with contiguous head_dim).
     k_lens: int32 CUDA tensor [B] or None.  The per-key modifiers select uvb_xattn_fwd_bf16."""
     global launch_count
@@ -296,9 +296,11 @@ def fmha_fwd(q, k, v, k_lens=None, softmax_scale=None, out=None, key_logit_scale
         raise ValueError("k_lens must be int32 [B] on the device")
     scale = float(D ** -0.5 if softmax_scale is None else softmax_scale)
     stream = _stream(q)
-    ws = _fmha_workspace(q.device, stream)
+    # split_units=False passes workspace = NULL: the schedule that never splits a query block over CTAs
+    ws = _fmha_workspace(q.device, stream) if split_units else None
     args = (B, Lq, Lk, N, _c.cast(_strides3(q), _vp), _c.cast(_strides3(k), _vp),
-            _c.cast(_strides3(v), _vp), _c.cast(_strides3(out), _vp), scale, ws.data_ptr(), ws.numel(), stream)
+            _c.cast(_strides3(v), _vp), _c.cast(_strides3(out), _vp), scale,
+            None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(), stream)
     if key_logit_scale is None and key_pv_weight is None and out_bias is None:
         _check(lib().uvb_fmha_fwd_bf16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(k_lens), *args))
     else:
