@@ -176,7 +176,9 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   // (then even fewer units than SMs keep every SM busy).
   const long long n_kv = (Lk + uvb::kBlockN - 1) / uvb::kBlockN;
   long long grid_x = units < sms ? units : sms;
-  if (workspace != nullptr && allow_split) {
+  // Splitting pays when a query block spans many key tiles; with a handful (cross-attention: 4) a partial
+  // costs almost as much as a whole block (Q load, 128 KiB partial through L2, merge), so those never split.
+  if (workspace != nullptr && allow_split && n_kv > kShortKeyTiles) {
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
       return fail(UVB_ERR_INVALID, "workspace must be 256-byte aligned");
     if (workspace_bytes < static_cast<int64_t>(fmha_ws_bytes(sms)))

@@ -426,7 +426,18 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     const float scale_log2 = p.scale_log2;
     const int ws_row = t * kBlockM + row;          // row inside the unit
     bool stored = false;
+    int pending_qb = -1;   // kQBufs == 2: query buffer whose O store was issued but not yet released
     int gstep = 0;
+    // With two query buffers the release of a buffer (its O store must have finished READING the staging
+    // area) is not needed before the producer loads the block after next, so the storing thread does not
+    // wait right after the store: it releases the buffer one softmax step into the next segment.
+    auto release_pending = [&]() {
+      if (pending_qb >= 0) {
+        tma_store_wait_read0();
+        mbar_arrive(&q_empty[2 * pending_qb + t]);
+        pending_qb = -1;
+      }
+    };
     if (p.timeline != nullptr && threadIdx.x == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -533,7 +544,11 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           if (lane == 0) mbar_arrive(&p_full[2 * t + h]);   // one barrier per 64-key half (split-P)
         }
         l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        if constexpr (kQBufs == 2) {
+          if (step == 0) release_pending();
+        }
       }
+      if constexpr (kQBufs == 2) release_pending();     // segments without steps
       gstep += n_steps;
 
       // ------------------------------------- segment epilogue -------------------------------------
@@ -705,11 +720,16 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             if (sch.rem_lo(gp + 1) != sch.rem_lo(gp)) st_release_gpu(p.flags + 2 * gp + t, 0u);
           }
         }
-        tma_store_wait_read0();          // the staging buffer may be overwritten by the next Q_t
-        mbar_arrive(&q_empty[2 * (si % kQBufs) + t]);
+        if constexpr (kQBufs == 2) {
+          pending_qb = si % kQBufs;
+        } else {
+          tma_store_wait_read0();          // the staging buffer may be overwritten by the next Q_t
+          mbar_arrive(&q_empty[si % kQBufs * 2 + t]);
+        }
         stored = true;
       }
     }
+    if constexpr (kQBufs == 2) release_pending();
     if (stored) tma_store_wait0();
     if (p.timeline != nullptr && threadIdx.x == 0)
       p.timeline[blockIdx.x * 32 + 1 + min(sch.n_seg, 30)] = globaltimer_ns();
