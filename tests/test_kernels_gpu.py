@@ -108,7 +108,9 @@ def test_head_scatter(ext):
 
 
 @pytest.mark.parametrize("b,lq,lk,n", [(1, 128, 128, 1), (1, 256, 384, 2), (2, 1950, 1950, 3), (1, 300, 77, 2),
-                                       (1, 1, 1, 1), (3, 129, 513, 1), (1, 1950, 512, 12)])
+                                       (1, 1, 1, 1), (3, 129, 513, 1), (1, 1950, 512, 12),
+                                       # SURVEY 8f rank 4 shapes: Wan-Animate image branch (257 keys), ti2v-5B (24 heads)
+                                       (1, 700, 257, 24), (2, 520, 520, 24)])
 def test_fmha_matches_oracle(ext, b, lq, lk, n):
     g = torch.Generator().manual_seed(lq * 7 + lk)
     q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))

@@ -121,6 +121,25 @@ def test_config1_block_attention_stack(realistic):
     _check(got_w, orc.cross_attention_text_weighted(x, ctx, prm_c, heads, 1.3, eps=EPS, bf16=False))
 
 
+def test_cfg_batched_forward_equals_two_single_forwards(small_case):
+    """the cond / uncond passes of classifier-free guidance batched into one B = 2 call
+    (different contexts, same latent) give exactly what two B = 1 calls give."""
+    c = small_case
+    freqs = orc.make_freqs(128).cuda()
+    sa = _module(mdl.WanSelfAttention, c["prm_self"], DIM, HEADS)
+    ca = _module(mdl.WanCrossAttention, c["prm_cross"], DIM, HEADS)
+    x1 = c["x"][:1].cuda()
+    x2 = torch.cat([x1, x1])
+    ctx2 = torch.stack([c["context"][0], torch.zeros_like(c["context"][0])]).cuda()      # cond, "empty prompt"
+    gs2, sl2 = c["grid_sizes"][:1].repeat(2, 1), c["seq_lens"][:1].repeat(2)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        s_b = sa(x2, sl2, gs2, freqs)
+        c_b = ca(x2, ctx2, None)
+        for i in range(2):
+            assert torch.equal(s_b[i:i + 1], sa(x1, sl2[:1], gs2[:1], freqs))
+            assert torch.equal(c_b[i:i + 1], ca(x1, ctx2[i:i + 1], None))
+
+
 def test_flash_attention_entry_point_dtype_contract():
     g = torch.Generator().manual_seed(4)
     q, k, v = (torch.randn(1, 200, 2, 128, generator=g) for _ in range(3))

@@ -212,13 +212,41 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
 
 template <typename InT, bool kPeers>
 int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
-  const long long units = 2LL * p.B * p.L;   // one warp group per (row, q|k)
+  const int dim = p.N * 128;
   const dim3 block(uvb::kNormRopeWarps * 32);
+  // q and k together (self-attention): one warp group per token, both rows in flight; UVB_PROLOGUE_PAIR=0
+  // keeps the one-row-per-group kernel (A/B hook)
+  static const bool allow_pair = [] {
+    const char* e = getenv("UVB_PROLOGUE_PAIR");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const bool pair = allow_pair && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
+                    p.row_scale == nullptr && sizeof(InT) == 2;
+  if (pair) {
+    const long long tokens = static_cast<long long>(p.B) * p.L;
+    auto blocks = [&](int wpr) {
+      const int per_cta = uvb::kNormRopeWarps / wpr;
+      return static_cast<unsigned>((tokens + per_cta - 1) / per_cta);
+    };
+    bool done = true;
+    switch (dim) {
+      case 1536: uvb::qk_norm_rope_pair_kernel<InT, 6, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
+      case 2048: uvb::qk_norm_rope_pair_kernel<InT, 8, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
+      case 3072: uvb::qk_norm_rope_pair_kernel<InT, 6, 2, kPeers><<<blocks(2), block, 0, stream>>>(p); break;
+      case 4096: uvb::qk_norm_rope_pair_kernel<InT, 8, 2, kPeers><<<blocks(2), block, 0, stream>>>(p); break;
+      case 5120: uvb::qk_norm_rope_pair_kernel<InT, 5, 4, kPeers><<<blocks(4), block, 0, stream>>>(p); break;
+      default: done = false; break;
+    }
+    if (done) {
+      UVB_CUDA(cudaGetLastError());
+      return UVB_OK;
+    }
+  }
+  const long long units = 2LL * p.B * p.L;   // one warp group per (row, q|k)
   auto blocks = [&](int wpr) {
     const int per_cta = uvb::kNormRopeWarps / wpr;
     return static_cast<unsigned>((units + per_cta - 1) / per_cta);
   };
-  const int dim = p.N * 128;
   switch (dim) {   // VPL * WPR = dim / 256
     case 1536: uvb::qk_norm_rope_kernel<InT, 6, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;
     case 2048: uvb::qk_norm_rope_kernel<InT, 8, 1, kPeers><<<blocks(1), block, 0, stream>>>(p); break;

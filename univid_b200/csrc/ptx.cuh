@@ -294,6 +294,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(reinterpret_cast<uint64_t&>(c)));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   float2 d;
   asm("add.rn.f32x2 %0, %1, %2;"

@@ -99,8 +99,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // WPR warps cooperate on one row (lane index `lane` in [0, 32*WPR)); their partial sums of squares
 // meet in shared memory behind a named barrier private to the row.  kPre selects the affine
 // pre-map x <- rscale * x + pre_bias (text-weighted context rows).
+template <typename InT, int VPL, int WPR>
+__device__ __forceinline__ void load_row(RowVec<InT> (&v)[VPL], const InT* __restrict__ in, int lane) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i].load(in + (lane + 32 * WPR * i) * 8);
+}
+
 template <typename InT, int VPL, int WPR, bool kPre>
-__device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const float* __restrict__ w,
+__device__ __forceinline__ void norm_rope_row(RowVec<InT> (&v)[VPL], const float* __restrict__ w,
                                               __nv_bfloat16* __restrict__ out_row,
                                               __nv_bfloat16* const* peers, long long out_off, int hpg,
                                               long long out_sg, int dim, float eps, bool rotate,
@@ -108,9 +114,6 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
                                               const float* __restrict__ pre_bias, int lane,
                                               float* red, int bar_id) {
   constexpr int kStride = 32 * WPR;
-  RowVec<InT> v[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) v[i].load(in + (lane + kStride * i) * 8);
 
   auto fetch = [&](int i, float* x) {
     v[i].unpack(x);
@@ -127,18 +130,19 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
     }
   };
 
-  float ss0 = 0.f, ss1 = 0.f;
+  // packed f32x2 arithmetic (FFMA2 / FMUL2): the kernel is co-limited by instruction issue
+  float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float x[8];
     fetch(i, x);
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
-      ss0 = fmaf(x[e], x[e], ss0);
-      ss1 = fmaf(x[e + 1], x[e + 1], ss1);
+      const float2 xx = make_float2(x[e], x[e + 1]);
+      ss2 = ffma2(xx, xx, ss2);
     }
   }
-  float ss = warp_sum(ss0 + ss1);
+  float ss = warp_sum(ss2.x + ss2.y);
   if constexpr (WPR > 1) {
     if ((lane & 31) == 0) red[lane >> 5] = ss;
     named_bar_sync(bar_id, kStride);
@@ -160,13 +164,14 @@ __device__ __forceinline__ void norm_rope_row(const InT* __restrict__ in, const 
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vec * 8));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vec * 8) + 1);
       const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float2 r2 = make_float2(rinv, rinv);
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
-        y[e] *= rinv;
-        y[e + 1] *= rinv;
-        RowVec<InT>::round_in2(y[e], y[e + 1]);
-        y[e] *= ww[e];
-        y[e + 1] *= ww[e + 1];
+        float2 t = fmul2(make_float2(y[e], y[e + 1]), r2);
+        RowVec<InT>::round_in2(t.x, t.y);
+        t = fmul2(t, make_float2(ww[e], ww[e + 1]));
+        y[e] = t.x;
+        y[e + 1] = t.y;
       }
     }
     uint32_t o[4];
@@ -328,17 +333,73 @@ qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
   const float* pre_bias = is_k ? p.pre_bias : nullptr;
   const float rscale = (is_k && p.row_scale != nullptr) ? p.row_scale[l] : 1.0f;
   if constexpr (VPL > 0) {
+    RowVec<InT> v[VPL];
+    load_row<InT, VPL, WPR>(v, src + in_off, lane);
     if (pre_bias != nullptr) {
-      norm_rope_row<InT, VPL, WPR, true>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
+      norm_rope_row<InT, VPL, WPR, true>(v, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
                                          rotate, cs, rscale, pre_bias, lane, red + group * WPR, 1 + group);
     } else {
-      norm_rope_row<InT, VPL, WPR, false>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
+      norm_rope_row<InT, VPL, WPR, false>(v, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
                                           rotate, cs, rscale, nullptr, lane, red + group * WPR, 1 + group);
     }
   } else {
     norm_rope_row_generic<InT>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
                                rscale, pre_bias, lane);
   }
+}
+
+// Self-attention form (q AND k given, no affine pre-map): one group of WPR warps per TOKEN.  The q row and the
+// k row are both loaded before either is processed (2 x VPL independent 128-bit loads per lane in flight:
+// a third more bytes in flight per SM than the one-row-per-warp kernel at two CTAs per SM), and the token's
+// (cos, sin) pairs and index arithmetic are shared by the two rows.
+template <typename InT, int VPL, int WPR, bool kPeers>
+__global__ void __launch_bounds__(kNormRopeWarps * 32, 2)
+qk_norm_rope_pair_kernel(const __grid_constant__ NormRopeParams p) {
+  __shared__ float red[2][kNormRopeWarps];
+  const int warp = threadIdx.x >> 5;
+  const int group = warp / WPR;
+  const int lane = threadIdx.x - group * (32 * WPR);
+  const long long row = static_cast<long long>(blockIdx.x) * (kNormRopeWarps / WPR) + group;
+  if (row >= static_cast<long long>(p.B) * p.L) return;
+  const int b = p.B == 1 ? 0 : static_cast<int>(row / p.L);
+  const int l = static_cast<int>(row - static_cast<long long>(b) * p.L);
+  const int dim = p.N * 128;
+  const long long in_off = row * dim;
+
+  RowVec<InT> vq[VPL], vk[VPL];
+  load_row<InT, VPL, WPR>(vq, static_cast<const InT*>(p.q_in) + in_off, lane);
+  load_row<InT, VPL, WPR>(vk, static_cast<const InT*>(p.k_in) + in_off, lane);
+
+  float cs[8];
+  bool rotate = false;
+  if (p.cos_sin != nullptr) {
+    const int gb = b < kMaxBatchGrid ? b : kMaxBatchGrid - 1;
+    const int gh = p.grid[gb][1], gw = p.grid[gb][2];
+    const int tok = p.tok_offset + l;
+    rotate = tok < p.grid[gb][0] * gh * gw;
+    if (rotate) {
+      const int pf = tok / (gh * gw), ph = (tok / gw) % gh, pw = tok % gw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int jj = 4 * (lane & 15) + i;
+        const int pos = jj < 22 ? pf : (jj < 43 ? ph : pw);
+        const float2 v = __ldg(p.cos_sin + pos * 64 + jj);
+        cs[2 * i] = v.x;
+        cs[2 * i + 1] = v.y;
+      }
+    }
+  }
+  if (!rotate) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+  }
+  const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
+  norm_rope_row<InT, VPL, WPR, false>(vq, p.wq, p.q_out + out_off, kPeers ? p.q_peer : nullptr, out_off, p.hpg,
+                                      p.out_sg, dim, p.eps, rotate, cs, 1.0f, nullptr, lane, red[0] + group * WPR,
+                                      1 + group);
+  norm_rope_row<InT, VPL, WPR, false>(vk, p.wk, p.k_out + out_off, kPeers ? p.k_peer : nullptr, out_off, p.hpg,
+                                      p.out_sg, dim, p.eps, rotate, cs, 1.0f, nullptr, lane, red[1] + group * WPR,
+                                      1 + group);
 }
 
 // Head-group scatter of an un-normalised tensor (v) into the Ulysses send layout; pure copy.
