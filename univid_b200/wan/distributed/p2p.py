@@ -48,6 +48,27 @@ def _align(n, a=256):
     return (n + a - 1) // a * a
 
 
+def exchange_layout(B, s, N, p, rank):
+    """Pure layout arithmetic of one rank's view of the exchange (unit-tested on the CPU against the oracle's
+    emulation of the reference all_to_all, tests/test_p2p_layout_cpu.py).  Offsets into an exchange buffer are
+    bytes; strides are bf16 elements.
+      q/k/v_recv of rank j = [B, p, s, n, 128]: rank `rank` stores element (b, l, h, d) of its head group j at
+          off_x + slot_bytes + 2 * (b * send_sb + l * send_sl + h * 128 + d)        inside rank j's buffer
+      o_recv of rank i = [B, s, N, 128]: rank `rank` stores rows [i*s, (i+1)*s) of its output at head offset
+          rank * n
+      flags: this rank's word inside every peer's flag area (qkv at byte 4*rank, o at 128 + 4*rank)."""
+    n = N // p
+    elems = B * s * N * 128                       # == B * L * n * 128
+    off_q = _FLAG_BYTES
+    off_k = off_q + _align(elems * 2)
+    off_v = off_k + _align(elems * 2)
+    off_o = off_v + _align(elems * 2)
+    return dict(n=n, elems=elems, off_q=off_q, off_k=off_k, off_v=off_v, off_o=off_o,
+                nbytes=off_o + _align(elems * 2), slot_bytes=rank * s * n * 128 * 2,
+                send_sb=p * s * n * 128, send_sl=n * 128, o_head_offset=rank * n,
+                qkv_flag_bytes=4 * rank, o_flag_bytes=_O_FLAG_OFF + 4 * rank)
+
+
 class UlyssesP2P:
     def __init__(self, B, s, N, device, group=None):
         self.group = group
@@ -58,12 +79,10 @@ class UlyssesP2P:
             raise ValueError(f"{N} heads cannot be split over {p} ranks")
         self.B, self.s, self.N, self.n, self.L = B, s, N, N // p, p * s
         self.device = device
-        elems = B * s * N * 128                       # == B * L * n * 128
-        self.off_q = _FLAG_BYTES
-        self.off_k = self.off_q + _align(elems * 2)
-        self.off_v = self.off_k + _align(elems * 2)
-        self.off_o = self.off_v + _align(elems * 2)
-        self.nbytes = self.off_o + _align(elems * 2)
+        lay = exchange_layout(B, s, N, p, self.rank)
+        elems = lay["elems"]
+        self.off_q, self.off_k, self.off_v, self.off_o = lay["off_q"], lay["off_k"], lay["off_v"], lay["off_o"]
+        self.nbytes = lay["nbytes"]
         lib = _ext.lib()
         with torch.cuda.device(device):
             base = ctypes.c_void_p()
@@ -82,14 +101,14 @@ class UlyssesP2P:
                 _ext._check(lib.uvb_sp_ipc_import(ctypes.create_string_buffer(handles[j], 64), ctypes.byref(ptr)))
                 self.peer_base.append(int(ptr.value))
         n, r = self.n, self.rank
-        slot = r * s * n * 128 * 2                    # byte offset of slot (b = 0, i = rank) in a peer's q/k/v_recv
+        slot = lay["slot_bytes"]                      # byte offset of slot (b = 0, i = rank) in a peer's q/k/v_recv
         self.q_peers = _ext.ptr_array([pb + self.off_q + slot for pb in self.peer_base])
         self.k_peers = _ext.ptr_array([pb + self.off_k + slot for pb in self.peer_base])
         self.v_peers = _ext.ptr_array([pb + self.off_v + slot for pb in self.peer_base])
         self.o_peers = _ext.ptr_array([pb + self.off_o for pb in self.peer_base])
-        self.qkv_flag_peers = _ext.ptr_array([pb + 4 * r for pb in self.peer_base])
-        self.o_flag_peers = _ext.ptr_array([pb + _O_FLAG_OFF + 4 * r for pb in self.peer_base])
-        self.send_sb, self.send_sl = p * s * n * 128, n * 128      # element strides of a slot inside [B, p, s, n, 128]
+        self.qkv_flag_peers = _ext.ptr_array([pb + lay["qkv_flag_bytes"] for pb in self.peer_base])
+        self.o_flag_peers = _ext.ptr_array([pb + lay["o_flag_bytes"] for pb in self.peer_base])
+        self.send_sb, self.send_sl = lay["send_sb"], lay["send_sl"]      # element strides of a slot inside [B, p, s, n, 128]
         raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=device)
         self._raw = raw
         view = lambda off, shape: raw[off:off + elems * 2].view(torch.bfloat16).view(shape)
