@@ -18,13 +18,13 @@ for c in "prol 1 1950 12 1 0 0" "prol 2 300 12 1 1 0" "prol 1 1000 40 1 0 0" "pr
   echo "-- $c"; timeout 120 $T $c 2>&1 | tail -3
 done | tee gpurun_out/kernels_$TAG.log
 echo "== ncu launch list of the bench command"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fmha_fwd_kernel|qk_norm_rope_kernel|head_scatter_kernel" -c 900 \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fmha_fwd_kernel|qk_norm_rope|head_scatter_kernel|block_glue" -c 900 \
     --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --skip-cpu --skip-denoise > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "launch list rows: $(wc -l < gpurun_out/launches_$TAG.csv)"
 echo "== ncu --set full: self-attention kernel, prologue kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_fmha_$TAG \
     $T fmha 1 32760 32760 12 -1 0 1 > gpurun_out/ncu_fmha_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:qk_norm_rope_kernel -s 1 -c 1 -f -o gpurun_out/prof_prol_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:qk_norm_rope -s 1 -c 1 -f -o gpurun_out/prof_prol_$TAG \
     $T prol 1 32760 12 1 0 1 > gpurun_out/ncu_prol_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_xattn_$TAG \
     $T fmha 1 32760 512 12 -1 0 1 > gpurun_out/ncu_xattn_$TAG.log 2>&1
