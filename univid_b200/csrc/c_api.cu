@@ -200,9 +200,9 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     return e != nullptr ? atoi(e) : 0;
   }();
   void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 0, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 0, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 4) kern = uvb::fmha_fwd_kernel<4, 1, 4, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 8) kern = uvb::fmha_fwd_kernel<4, 1, 8, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 3) kern = uvb::fmha_fwd_kernel<4, 1, 3, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 4) kern = uvb::fmha_fwd_kernel<3, 1, 4, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 8) kern = uvb::fmha_fwd_kernel<3, 1, 8, kKeyMod>;
+  if (!short_keys && !kKeyMod && poly == 3) kern = uvb::fmha_fwd_kernel<3, 1, 3, kKeyMod>;
   const int smem = short_keys ? uvb::FmhaSmem<3, 2>::kDynBytes : uvb::FmhaSmem<4, 1>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<dim3(static_cast<unsigned>(grid_x)), uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);

@@ -20,11 +20,14 @@
 //   warp  8     tcgen05.mma issuer (one elected thread) + TMEM allocator     setmaxnreg.dec
 //   warp  9     TMA producer (one elected thread)                            setmaxnreg.dec
 //   warps 10-11 idle (they only exist so the third warpgroup can give its registers away)
-// TMEM (512 columns x 128 lanes):  S0 | S1 | O0 | O1.  P (bf16) aliases the first 64 columns of its S and
-// is consumed as the A operand of the PV MMA straight from TMEM; it is handed over in two 64-key halves
-// (split-P) so the PV MMA starts while the softmax still works on the second half.  K/V tiles
-// (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem for the segment and its
-// buffer is reused to stage O for the TMA store.
+// TMEM (512 columns x 128 lanes):  S0 | S1 | O0 | O1.  P (bf16) is handed to the PV MMA in two 64-key halves
+// (split-P) so the PV starts while the softmax still works on the second half.  The first half aliases the
+// first 32 columns of its S and is the A operand straight from TMEM.  For long key sequences (kQBufs == 1) the
+// second half goes through a 16 KiB shared-memory panel per tile instead: once the first half has arrived the
+// whole of S_t sits in the softmax registers, so the NEXT score tile Q_t K_{j+1}^T is issued right after the
+// first PV half -- QK^T leaves the softmax -> MMA -> softmax dependency chain and only 64 keys of PV remain
+// on it.  K/V tiles (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem for the
+// segment and its buffer is reused to stage O for the TMA store.
 //
 // Ordering facts the protocol relies on: tcgen05 MMAs issued by one thread execute in order, so
 // S_t(s+1) overwriting the buffer that held P_t(s) is safe once PV_t(s) has been issued before it; the
@@ -60,7 +63,11 @@ template <int kStages, int kQBufs>
 struct FmhaSmem {
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQBufs * kQTiles * kTileBytes;
-  static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
+  // kQBufs == 1 (long key sequences): the second 64-key half of P goes through shared memory (16 KiB per query
+  // tile, K-major SWIZZLE_128B like Q) so that the next score tile can be issued before it is consumed
+  static constexpr bool kPSmem = kQBufs == 1;
+  static constexpr int kPOff = kKvOff + kStages * kTileBytes;
+  static constexpr int kBarOff = kPOff + (kPSmem ? kQTiles * kHalfTile : 0);
   // barriers: q_full[B][2] q_empty[B][2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
   static constexpr int kNumBars = 4 * kQBufs + 2 * kStages + 10;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
@@ -149,18 +156,18 @@ struct FmhaSched {
   }
 };
 
-// exp2 of 64 scores of one row -> 32 packed bf16x2 probabilities + partial row sums.  One pair in every
+// exp2 of 2*kPairs scores of one row -> kPairs packed bf16x2 probabilities + partial row sums.  One pair in every
 // kPolyEvery goes through the FMA-pipe polynomial instead of MUFU.EX2 (0 = never): the XU pipe does 16
 // exp2/clk/SM, exactly the rate at which the tensor pipe consumes a 128x128 tile, so offloading a share
 // of them is what lets the softmax keep ahead of the MMAs.
-template <int kPolyEvery, bool kKeyMod>
-__device__ __forceinline__ void softmax_exp64(const uint32_t* sr, float scale_log2, float neg_ms,
-                                              float2& sum_a, float2& sum_b, uint32_t* pk,
-                                              const float* pvw) {
+template <int kPairs, int kPolyEvery, bool kKeyMod>
+__device__ __forceinline__ void softmax_exp(const uint32_t* sr, float scale_log2, float neg_ms,
+                                            float2& sum_a, float2& sum_b, uint32_t* pk,
+                                            const float* pvw) {
   const float2 sc = make_float2(scale_log2, scale_log2);
   const float2 nm = make_float2(neg_ms, neg_ms);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < kPairs; ++i) {
     const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc, nm);
     float2 e;
     if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
@@ -197,6 +204,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   asm volatile("" : "+l"(smem));
   uint8_t* smem_q = smem + SM::kQOff;
   uint8_t* smem_kv = smem + SM::kKvOff;
+  uint8_t* smem_p = smem + SM::kPOff;
+  constexpr bool kPSmem = SM::kPSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
   uint64_t* q_full = bars;                       // [buf][tile]  TMA -> MMA: Q_t of the segment landed
   uint64_t* q_empty = bars + 2 * kQBufs;         // [buf][tile]  softmax -> TMA: Q_t / O staging is free again
@@ -340,6 +349,20 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       };
       // O_t (+)= P_t V : A = P from TMEM (8 columns per 16 keys), B = V rows, MN-major: 16 keys = 2 KiB
       // per K-step, the two 64-dim panels are kHalfTile apart (LBO), 8-key groups 1 KiB apart (SBO)
+      // second half of P from shared memory (kPSmem): A K-major like Q, keys 64..127 of the V tile
+      const uint64_t p_desc = umma_desc_sw128(smem_u32(smem_p), 16, 1024);
+      auto issue_pv_smem = [&](int t, int v_ring) {
+        const uint64_t va = v_desc + (v_ring % kStages) * kTile16;
+        const uint64_t pa = p_desc + t * (kHalfTile >> 4);
+        const uint32_t d = tmem_base + 256 + t * kHeadDim;
+        if (elect_one()) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_ss(d, pa + ((k4 * 32) >> 4), va + (4 + k4) * (2048 >> 4), idesc_pv, 1u);
+          }
+        }
+        __syncwarp();
+      };
       auto issue_pv = [&](int t, int v_ring, bool first_step, int kk0) {   // 4 K-steps = 64 keys from kk0
         const uint64_t va = v_desc + (v_ring % kStages) * kTile16;
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
@@ -395,16 +418,34 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             mbar_wait(&p_full[2 * t + 0], par);
             tc_fence_after();
             issue_pv(t, v_ring, step == 0, 0);
-            mbar_wait(&p_full[2 * t + 1], par);
-            tc_fence_after();
-            issue_pv(t, v_ring, step == 0, 4);
-            commit(&pv_done[t]);
-            if (more) {
-              if (t == 0) wait_full(k_ring);
-              issue_qk(2 * qb + t, t, k_ring);
-              commit(&s_full[t]);
+            if constexpr (kPSmem) {
+              // The first half of P has arrived, so all of S_t sits in the softmax registers, and the PV just
+              // issued reads P[0, 32) before anything issued after it runs: the next score tile can go out NOW,
+              // while the softmax still exponentiates the second half (which it hands over through shared
+              // memory, not through S_t).  Only the last 64 keys of PV stay on the softmax -> MMA -> softmax
+              // dependency chain; QK^T leaves it.
+              if (more) {
+                if (t == 0) wait_full(k_ring);
+                issue_qk(2 * qb + t, t, k_ring);
+                commit(&s_full[t]);
+              }
+              mbar_wait(&p_full[2 * t + 1], par);
+              tc_fence_after();
+              issue_pv_smem(t, v_ring);
+              commit(&pv_done[t]);
+              if (!more) commit(&o_full[t]);
             } else {
-              commit(&o_full[t]);
+              mbar_wait(&p_full[2 * t + 1], par);
+              tc_fence_after();
+              issue_pv(t, v_ring, step == 0, 4);
+              commit(&pv_done[t]);
+              if (more) {
+                if (t == 0) wait_full(k_ring);
+                issue_qk(2 * qb + t, t, k_ring);
+                commit(&s_full[t]);
+              } else {
+                commit(&o_full[t]);
+              }
             }
           }
           commit(&kv_empty[v_ring % kStages]);
@@ -534,12 +575,31 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          uint32_t pk[32];
-          softmax_exp64<kPolyEvery, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
-                                             pvw == nullptr ? nullptr : pvw + 64 * h);
-          tmem_st_x32(tS + 32 * h, pk);
-          tmem_wait_st();
-          tc_fence_before();
+          if (kPSmem && h == 1) {
+            // second half -> shared memory, row `row` of the K-major SWIZZLE_128B panel of this tile (the
+            // PV of the previous step must have finished reading the panel: pv_done, long since complete).
+            // (Handing the generic->async proxy fence and the arrive to a helper warp behind a named barrier
+            // takes ~230 cycles per step off this warp but adds as much to the hand-off latency of the last
+            // PV, which is on the dependency chain: measured slower.)
+            uint32_t pk[32];
+            softmax_exp<32, kPolyEvery, kKeyMod>(sr + 64, scale_log2, neg_ms, sum_a, sum_b, pk,
+                                                 pvw == nullptr ? nullptr : pvw + 64);
+            if (gstep + step > 0) mbar_wait(&pv_done[t], par ^ 1);
+            uint8_t* prow = smem_p + t * kHalfTile + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
+                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            fence_proxy_async_smem();
+          } else {
+            uint32_t pk[32];
+            softmax_exp<32, kPolyEvery, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
+                                                 pvw == nullptr ? nullptr : pvw + 64 * h);
+            tmem_st_x32(tS + 32 * h, pk);
+            tmem_wait_st();
+            tc_fence_before();
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[2 * t + h]);   // one barrier per 64-key half (split-P)
         }
