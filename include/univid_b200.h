@@ -179,6 +179,21 @@ int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, con
                        const int64_t* v_strides, const int64_t* o_strides, float scale,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* y = act(x . w^T + bias): the nn.Linear layers of the DiT block around the attention core, under bf16 autocast
+ * (SURVEY.md sec. 8f, rank 2).  Replaces: F.linear as called by WanSelfAttention / WanCrossAttention q, k, v, o
+ * (model.py:119-122, :137-139, :152-154, :170-173, :178-179) and by the block's ffn (model.py:212-214, :256),
+ * where act = UVB_ACT_GELU_TANH also replaces nn.GELU(approximate='tanh') (model.py:213) on the first ffn layer.
+ *
+ *   x [M, K] bf16 (leading dimension ldx elements), w [N, K] bf16 (nn.Linear.weight layout, ldw),
+ *   bias [N] fp32 or NULL (autocast rounds the bias to bf16 before the add: pass the rounded values),
+ *   y [M, N] bf16 (ldy).  N, K and the leading dimensions are multiples of 8; pointers 16-byte aligned.
+ *   Accumulation in fp32; the biased sum is rounded to bf16 (the Linear's output) and, with GELU, the activation
+ *   is evaluated in fp32 on that rounded value and rounded again -- the reference's rounding points.
+ */
+enum uvb_act { UVB_ACT_NONE = 0, UVB_ACT_GELU_TANH = 1 };
+int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
+                    int64_t ldw, int64_t ldy, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

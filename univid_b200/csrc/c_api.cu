@@ -9,6 +9,7 @@
 #include "fmha_fwd_sm100.cuh"
 #include "qk_norm_rope.cuh"
 #include "block_glue.cuh"
+#include "gemm_bf16_sm100.cuh"
 
 namespace {
 
@@ -89,6 +90,72 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const 
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return UVB_OK;
+}
+
+// row-major bf16 matrix [rows, cols] with leading dimension ld (elements) as a 2-D TMA map, dims (cols, rows)
+int make_matrix_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return fail(UVB_ERR_INVALID, "matrix base pointer must be 16-byte aligned");
+  if (ld < cols || ld % 8 != 0) return fail(UVB_ERR_INVALID, "leading dimension %lld must be >= %d and a multiple of 8",
+                                             static_cast<long long>(ld), cols);
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return UVB_OK;
+}
+
+template <int kCtas>
+int launch_gemm(uvb::GemmParams& p, const void* x, const void* w, void* y, int64_t ldx, int64_t ldw, int64_t ldy,
+                int sms, cudaStream_t stream) {
+  using SM = uvb::GemmSmem<kCtas>;
+  int rc;
+  if ((rc = make_matrix_map(&p.tm_a, x, p.M, p.K, ldx, uvb::kGemmBM)) != UVB_OK) return rc;
+  if ((rc = make_matrix_map(&p.tm_b, w, p.N, p.K, ldw, uvb::kGemmBN / kCtas)) != UVB_OK) return rc;
+  if ((rc = make_matrix_map(&p.tm_c, y, p.M, p.N, ldy, uvb::kGemmBM)) != UVB_OK) return rc;
+  p.n_m = (p.M + uvb::kGemmBM * kCtas - 1) / (uvb::kGemmBM * kCtas);
+  p.n_n = (p.N + uvb::kGemmBN - 1) / uvb::kGemmBN;
+  const long long tiles = static_cast<long long>(p.n_m) * p.n_n;
+  if (tiles > 0x7fffffffLL) return fail(UVB_ERR_INVALID, "too many output tiles");
+  auto kern = uvb::gemm_bf16_kernel<kCtas>;
+  UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(uvb::kGemmThreads);
+  cfg.dynamicSmemBytes = SM::kDynBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  long long workers = sms / kCtas;
+  if (kCtas == 2) {
+    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent pairs: no more clusters than can be resident at once (one per TPC)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+      int n = 0;
+      UVB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max_clusters = n;
+    }
+    if (max_clusters <= 0) return fail(UVB_ERR_UNSUPPORTED, "no CTA pair of the GEMM kernel fits on this device");
+    if (workers > max_clusters) workers = max_clusters;
+  }
+  if (workers > tiles) workers = tiles;
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtas));
+  UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return UVB_OK;
 }
 
@@ -541,6 +608,33 @@ int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, con
   return launch_fmha<true>(q, k, v, o, k_lens, key_logit_scale, key_pv_weight, out_bias, B, Lq, Lk,
                            N, q_strides, k_strides, v_strides, o_strides, scale, workspace,
                            workspace_bytes, stream);
+}
+
+int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
+                    int64_t ldw, int64_t ldy, int act, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr) return fail(UVB_ERR_INVALID, "null matrix pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return fail(UVB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
+  if (N % 8 != 0 || K % 8 != 0) return fail(UVB_ERR_INVALID, "N=%d and K=%d must be multiples of 8", N, K);
+  if (act != UVB_ACT_NONE && act != UVB_ACT_GELU_TANH) return fail(UVB_ERR_INVALID, "bad activation %d", act);
+  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 3) != 0) return fail(UVB_ERR_INVALID, "bias alignment");
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+  int sms = 0;
+  if ((rc = sm_count(&sms)) != UVB_OK) return rc;
+  uvb::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.act = act;
+  // Tuning hook (read once): UVB_GEMM_CTAS=1 keeps one CTA per tile instead of CTA pairs (cta_group::2)
+  static const int ctas = [] {
+    const char* e = getenv("UVB_GEMM_CTAS");
+    return e != nullptr && atoi(e) == 1 ? 1 : 2;
+  }();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return ctas == 2 ? launch_gemm<2>(p, x, w, y, ldx, ldw, ldy, sms, st) : launch_gemm<1>(p, x, w, y, ldx, ldw, ldy, sms, st);
 }
 
 }  // extern "C"

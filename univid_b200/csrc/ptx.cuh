@@ -146,10 +146,15 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// all but the most recently committed store group have finished reading their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 // L2 eviction policies (createpolicy encodings, as used for TMA cache hints)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 

@@ -2,6 +2,7 @@
 // Usage: uvb_test <case> [args]   -- one case per process so a trapped kernel cannot poison the next.
 //   fmha  B Lq Lk N klen keymod iters     compare with a naive fp32 kernel (if Lq*Lk small) and time
 //   prol  B L N rope dtype iters          compare with a double-precision host reference and time
+//   gemm  M N K act iters                 uvb_linear_bf16 against a naive fp32-accumulate kernel, and time
 // Test infrastructure only; nothing here is part of the product library.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -440,13 +441,143 @@ static int run_prol(int argc, char** argv) {
   return status;
 }
 
+// one thread per output element: fp32 accumulation in k order, bias, bf16 rounding, optional tanh-GELU in fp32
+__global__ void naive_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, float* y, int M,
+                             int N, int K, int act) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int n = idx % N;
+  const long long m = idx / N;
+  const __nv_bfloat16* xr = x + m * K;
+  const __nv_bfloat16* wr = w + (long long)n * K;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(xr[k]) * __bfloat162float(wr[k]);
+  if (bias) acc += bias[n];
+  float v = __bfloat162float(__float2bfloat16(acc));
+  if (act == 1) v = 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
+  y[idx] = v;
+}
+
+static int run_gemm(int argc, char** argv) {
+  if (argc < 7) {
+    printf("gemm M N K act iters\n");
+    return 2;
+  }
+  const int M = atoi(argv[2]), N = atoi(argv[3]), K = atoi(argv[4]), act = atoi(argv[5]), iters = atoi(argv[6]);
+  const size_t nx = (size_t)M * K, nw = (size_t)N * K, ny = (size_t)M * N;
+  std::vector<__nv_bfloat16> hx(nx), hw(nw);
+  std::vector<float> hb(N);
+  const float ws = 1.0f / sqrtf((float)K);
+  for (auto& v : hx) v = __float2bfloat16(nrand());
+  for (auto& v : hw) v = __float2bfloat16(nrand() * ws);
+  for (auto& v : hb) v = __bfloat162float(__float2bfloat16(0.5f * frand()));
+  __nv_bfloat16 *dx, *dw, *dy;
+  float *db, *dref;
+  CK(cudaMalloc(&dx, nx * 2));
+  CK(cudaMalloc(&dw, nw * 2));
+  CK(cudaMalloc(&dy, ny * 2));
+  CK(cudaMalloc(&db, N * 4));
+  CK(cudaMemcpy(dx, hx.data(), nx * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), nw * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, hb.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dy, 0x7f, ny * 2));
+  auto launch = [&]() { return uvb_linear_bf16(dx, dw, db, dy, M, N, K, K, K, N, act, nullptr); };
+  int rc = launch();
+  if (rc != 0) {
+    printf("FAIL launch rc=%d: %s\n", rc, uvb_last_error());
+    return 1;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("FAIL kernel: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  int status = 0;
+  if ((double)M * N * K <= 6e11) {
+    CK(cudaMalloc(&dref, ny * 4));
+    naive_linear<<<(unsigned)((ny + 255) / 256), 256>>>(dx, dw, db, dref, M, N, K, act);
+    CK(cudaDeviceSynchronize());
+    std::vector<__nv_bfloat16> ho(ny);
+    std::vector<float> hr(ny);
+    CK(cudaMemcpy(ho.data(), dy, ny * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hr.data(), dref, ny * 4, cudaMemcpyDeviceToHost));
+    double maxrel = 0, dot = 0, na = 0, nb = 0;
+    size_t worst = 0, exact = 0, bad = 0;
+    for (size_t i = 0; i < ny; ++i) {
+      const double a = __bfloat162float(ho[i]), r = hr[i];
+      const double rr = __bfloat162float(__float2bfloat16((float)r));
+      if (a == rr) ++exact;
+      const double d = fabs(a - r) / fmax(1.0, fabs(r));
+      if (!(d <= 1.6e-2)) ++bad;
+      if (!(d <= maxrel)) {
+        maxrel = d;
+        worst = i;
+      }
+      dot += a * r;
+      na += a * a;
+      nb += r * r;
+    }
+    const double cosv = dot / (sqrt(na) * sqrt(nb) + 1e-30);
+    const bool ok = bad == 0 && cosv >= 0.99999;
+    printf("%s gemm M=%d N=%d K=%d act=%d: max_err=%.3e cos=%.8f bitexact=%.4f bad=%zu", ok ? "PASS" : "FAIL", M, N, K,
+           act, maxrel, cosv, (double)exact / ny, bad);
+    if (!ok) {
+      printf("  worst at m=%zu n=%zu got=%f ref=%f\n", worst / N, worst % N, __bfloat162float(ho[worst]), hr[worst]);
+      printf("  bad elements per (128-row, 64-col) block, first 8 x 8 blocks:\n");
+      for (int bm = 0; bm < 8 && bm * 128 < M; ++bm) {
+        printf("   rows %4d:", bm * 128);
+        for (int bn = 0; bn < 8 && bn * 64 < N; ++bn) {
+          int cnt = 0;
+          for (int r = bm * 128; r < (bm + 1) * 128 && r < M; ++r)
+            for (int c = bn * 64; c < (bn + 1) * 64 && c < N; ++c) {
+              const double a = __bfloat162float(ho[(size_t)r * N + c]), rf = hr[(size_t)r * N + c];
+              if (!(fabs(a - rf) / fmax(1.0, fabs(rf)) <= 1.6e-2)) ++cnt;
+            }
+          printf(" %5d", cnt);
+        }
+        printf("\n");
+      }
+      status = 1;
+    }
+    printf("\n");
+  }
+  if (iters > 0 && status == 0) {
+    // rotate over several input/weight sets? x (M*K) is >= L2 only for the big shapes; flush L2 between iterations
+    const size_t fb = 256u << 20;
+    void* flush;
+    CK(cudaMalloc(&flush, fb));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f, tot = 0;
+    for (int i = 0; i < iters; ++i) {
+      CK(cudaMemsetAsync(flush, i, fb));
+      CK(cudaEventRecord(e0));
+      launch();
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      best = fmin(best, ms);
+      tot += ms;
+    }
+    const double flop = 2.0 * M * (double)N * K;
+    printf("TIME gemm M=%d N=%d K=%d act=%d: best %.3f ms (%.1f TFLOP/s)  mean %.3f ms (%.1f TFLOP/s)\n", M, N, K, act,
+           best, flop / best * 1e-9, tot / iters, flop / (tot / iters) * 1e-9);
+  }
+  return status;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
-    printf("usage: uvb_test fmha|prol ...\n");
+    printf("usage: uvb_test fmha|prol|gemm ...\n");
     return 2;
   }
   if (!strcmp(argv[1], "fmha")) return run_fmha(argc, argv);
   if (!strcmp(argv[1], "prol")) return run_prol(argc, argv);
+  if (!strcmp(argv[1], "gemm")) return run_gemm(argc, argv);
   printf("unknown case %s\n", argv[1]);
   return 2;
 }
