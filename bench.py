@@ -292,12 +292,12 @@ def run_native_arm(args, cfg_key):
     value = flop_step / (ms_kernel * 1e-3) * 1e-12
 
     roofline, roofline_prologue = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if world == 1 and fmha_events:
         durs = [a.elapsed_time(b) for a, b in fmha_events]
         avg = sum(durs) / len(durs)
         achieved = fs / (avg * 1e-3) * 1e-12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(cfg_key, {}).get("fmha_dram_bytes_per_launch")
         roofline = {"kernel": "fmha_fwd_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
@@ -313,6 +313,36 @@ def run_native_arm(args, cfg_key):
                              "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"],
                              "peak_source": peaks["source"] + " copy bandwidth", "avg_launch_ms": pavg,
                              "bytes_per_launch": pbytes, "traffic": None}
+
+    # ---------------- the block's largest GEMM (ffn[0] + tanh-GELU), timed live -----
+    roofline_gemm = None
+    if world == 1:
+        ffn = cfg["ffn"]
+        xg = sets[0]["q"].view(s, dim)
+        wg = (torch.randn(ffn, dim, device=dev, generator=g) / dim ** 0.5).to(bf)
+        bg = torch.zeros(ffn, device=dev)
+        og = torch.empty(s, ffn, dtype=bf, device=dev)          # x + out >> L2: every launch streams from HBM
+        for _ in range(3):
+            _ext.linear(xg, wg, bg, act=_ext.ACT_GELU_TANH, out=og)
+        torch.cuda.synchronize()
+        n_g = 20
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(n_g):
+            _ext.linear(xg, wg, bg, act=_ext.ACT_GELU_TANH, out=og)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / n_g
+        gflop = 2.0 * s * ffn * dim
+        roofline_gemm = {"kernel": "gemm_bf16_kernel (ffn[0] + bias + tanh-GELU)", "bound": "tensor",
+                         "achieved": gflop / (gms * 1e-3) * 1e-12, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_sustained"],
+                         "frac_of_burst_peak": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_burst"],
+                         "peak_source": peaks["source"] + " sustained bf16 (20 launches back to back)",
+                         "avg_launch_ms": gms, "flop_per_launch": gflop, "shape_mnk": [s, ffn, dim],
+                         "traffic": (json.load(open(tpath)).get(cfg_key, {}).get("gemm_ffn0_dram_bytes_per_launch")
+                                     if os.path.exists(tpath) else None)}
+        del wg, og
 
     # ---------------- e2e: public module API from pinned host memory ---------------------------------
     torch.manual_seed(0)
@@ -409,6 +439,7 @@ def run_native_arm(args, cfg_key):
             "attention_flop_per_step": flop_step,
             "denoise_step_ms": denoise_ms,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prologue": roofline_prologue,
+            "roofline_gemm": roofline_gemm,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -14,11 +14,12 @@ tail -3 gpurun_out/bench_sweep_$TAG.err
 echo "== kernel battery (prologue + cross)"
 T=univid_b200/csrc/tests/uvb_test
 for c in "prol 1 1950 12 1 0 0" "prol 2 300 12 1 1 0" "prol 1 1000 40 1 0 0" "prol 1 500 24 1 0 0" "prol 1 500 10 1 0 0" \
-         "prol 1 32760 12 1 0 20" "prol 1 75600 40 1 0 10" "prol 1 27280 24 1 0 10" "fmha 1 32760 512 12 -1 0 10" "fmha 1 32760 32760 12 -1 0 5"; do
+         "prol 1 32760 12 1 0 20" "prol 1 75600 40 1 0 10" "prol 1 27280 24 1 0 10" "fmha 1 32760 512 12 -1 0 10" "fmha 1 32760 32760 12 -1 0 5" \
+         "gemm 1000 1536 1536 1 0" "gemm 32760 1536 1536 0 10" "gemm 32760 8960 1536 1 5" "gemm 32760 1536 8960 0 5" "gemm 75600 5120 5120 0 3"; do
   echo "-- $c"; timeout 120 $T $c 2>&1 | tail -3
 done | tee gpurun_out/kernels_$TAG.log
 echo "== ncu launch list of the bench command"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fmha_fwd_kernel|qk_norm_rope|head_scatter_kernel|block_glue" -c 900 \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fmha_fwd_kernel|qk_norm_rope|head_scatter_kernel|block_glue|gemm_bf16" -c 900 \
     --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --skip-cpu --skip-denoise > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "launch list rows: $(wc -l < gpurun_out/launches_$TAG.csv)"
 echo "== ncu --set full: self-attention kernel, prologue kernel"
@@ -28,4 +29,12 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:qk_n
     $T prol 1 32760 12 1 0 1 > gpurun_out/ncu_prol_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd_kernel -s 1 -c 1 -f -o gpurun_out/prof_xattn_$TAG \
     $T fmha 1 32760 512 12 -1 0 1 > gpurun_out/ncu_xattn_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 1 -c 1 -f -o gpurun_out/prof_gemm_$TAG \
+    $T gemm 32760 8960 1536 1 1 > gpurun_out/ncu_gemm_$TAG.log 2>&1
+echo "== ncu launch list of one full-size DiT block (every kernel, library ones included)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_block_$TAG.csv \
+    python scripts/ncu_block.py > gpurun_out/ncu_block_$TAG.log 2>&1
+echo "block launch list rows: $(wc -l < gpurun_out/launches_block_$TAG.csv)"
+echo "== denoise step by category (CUDA events)"
+python scripts/profile_denoise.py > gpurun_out/denoise_profile_$TAG.log 2>&1; cat gpurun_out/denoise_profile_$TAG.log
 ls -la gpurun_out | tail -20

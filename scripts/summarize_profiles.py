@@ -83,6 +83,36 @@ def main():
         for (name, grid), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             lines.append(f"| `{name}` | {grid} | {n} | {t:.3f} | {100 * t / tot:.1f}% | {t / n * 1e3:.1f} |")
 
+    bpath = os.path.join(src, f"launches_block_{tag}.csv")
+    if os.path.exists(bpath):
+        shutil.copy(bpath, dst)
+        # keep the second pass only (after the second marker fill kernel)
+        rows = list(csv.reader(open(bpath)))
+        hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+        hdr, data = rows[hi], rows[hi + 1:]
+        ki, mi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        # the block input x is created by a normal_ kernel etc.; passes are separated by 1-element fill kernels
+        gi = hdr.index("Grid Size")
+        marks = [i for i, r in enumerate(data) if len(r) > mi and "fill" in r[ki].lower() and r[gi].replace(" ", "") in ("(1,1,1)", "1,1,1")]
+        start = marks[-1] + 1 if marks else 0
+        agg = collections.OrderedDict()
+        for r in data[start:]:
+            if len(r) <= mi:
+                continue
+            v = float(r[mi].replace(",", ""))
+            ms = v / 1e6 if r[ui].startswith("n") else (v / 1e3 if r[ui].startswith("u") else v)
+            name = r[ki].split("(")[0]
+            name = name if len(name) < 90 else name[:87] + "..."
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += ms
+        tot = sum(a[1] for a in agg.values()) or 1.0
+        lines.append(f"\n## ncu launch list of ONE full-size DiT block forward, 1.3B config, 32 760 tokens (launches_block_{tag}.csv, second pass; every kernel, cold-cache, serialised)\n")
+        lines.append("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            lines.append(f"| `{name}` | {n} | {t:.3f} | {100 * t / tot:.1f}% |")
+        lines.append(f"| total | {sum(a[0] for a in agg.values())} | {tot:.3f} | |")
+
     traffic = {}
     for rep in sorted(glob.glob(os.path.join(src, f"prof_*_{tag}.ncu-rep"))):
         name = os.path.basename(rep)[:-len(".ncu-rep")]
@@ -111,6 +141,8 @@ def main():
                 cur["1.3B"]["source"] = f"profiles/{tag}/{k}_raw.csv"
             if k.startswith("prof_prol_"):
                 cur.setdefault("1.3B", {})["prologue_dram_bytes_per_launch"] = v
+            if k.startswith("prof_gemm_"):
+                cur.setdefault("1.3B", {})["gemm_ffn0_dram_bytes_per_launch"] = v
         json.dump(cur, open(tj, "w"), indent=1)
     open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))

@@ -154,3 +154,27 @@ def test_grad_mode_is_refused():
         _ext._no_grad_only(t)
     with torch.no_grad():
         _ext._no_grad_only(t)
+
+
+def test_lin_helper_routes_cpu_and_wrapped_modules_through_the_module():
+    """_lin / _ffn_forward (SURVEY.md sec. 8f rank 2 host side): anything that is not a plain nn.Linear on CUDA in the
+    inference configuration is computed by the module itself; the bf16 operand cache follows parameter updates."""
+    import torch
+    import torch.nn as nn
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    lin = nn.Linear(16, 24)
+    x = torch.randn(3, 16)
+    assert not mdl._gemm_ok(lin, x)
+    assert torch.equal(mdl._lin(lin, x), lin(x))
+    assert torch.equal(mdl._lin(lin, x, act=1), torch.nn.functional.gelu(lin(x), approximate="tanh"))
+    ffn = nn.Sequential(nn.Linear(16, 32), nn.GELU(approximate="tanh"), nn.Linear(32, 16))
+    assert torch.equal(mdl._ffn_forward(ffn, x), ffn(x))
+    w, b = mdl._linear_operands(lin)
+    assert w.dtype == torch.bfloat16 and b.dtype == torch.float32
+    assert torch.equal(w, lin.weight.detach().to(torch.bfloat16))
+    assert torch.equal(b, lin.bias.detach().to(torch.bfloat16).float())     # autocast rounds the bias to bf16
+    assert mdl._linear_operands(lin)[0] is w                                 # cached
+    with torch.no_grad():
+        lin.weight.mul_(3.0)
+    w2, _ = mdl._linear_operands(lin)
+    assert w2 is not w and torch.equal(w2, lin.weight.detach().to(torch.bfloat16))

@@ -16,9 +16,9 @@ EXPORTS = (
     "uvb_fmha_fwd_bf16", "uvb_fmha_workspace_bytes", "uvb_xattn_fwd_bf16", "uvb_debug_fmha_timeline",
     "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
-    "uvb_sp_wait", "uvb_block_glue",
+    "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16",
 )
-ABI_VERSION = 103
+ABI_VERSION = 104
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -77,6 +77,8 @@ def lib():
     L.uvb_sp_wait.argtypes = [_vp, _i, _u32, _vp]
     L.uvb_block_glue.restype = _i
     L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _f, _vp]
+    L.uvb_linear_bf16.restype = _i
+    L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
     if L.uvb_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB_PATH} has ABI version {L.uvb_version()}, expected {ABI_VERSION}: rebuild it "
                            "with `python -m univid_b200.build --force`")
@@ -395,3 +397,41 @@ def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, 
                                 _stream(x)))
     launch_count += 1
     return x_new, h
+
+
+ACT_NONE, ACT_GELU_TANH = 0, 1
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, out=None):
+    """y = act(x @ weight.T + bias) (uvb_linear_bf16): x bf16 [..., K] with dense rows, weight bf16 [N, K]
+    (nn.Linear layout), bias fp32 [N] (already rounded to bf16 values when mirroring autocast) or None.
+    Returns bf16 [..., N]."""
+    global launch_count
+    _require_cuda(x, weight, bias)
+    _no_grad_only(x, weight, bias)
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise NotImplementedError(f"linear computes in bf16; got x {x.dtype}, weight {weight.dtype}")
+    if weight.dim() != 2 or x.size(-1) != weight.size(1):
+        raise ValueError(f"linear: x [..., {x.size(-1)}] does not match weight {tuple(weight.shape)}")
+    N, K = weight.shape
+    if N % 8 != 0 or K % 8 != 0:
+        raise NotImplementedError(f"linear: N={N} and K={K} must be multiples of 8")
+    if weight.stride(1) != 1:
+        weight = weight.contiguous()
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.size(0)
+    if bias is not None:
+        if bias.numel() != N:
+            raise ValueError("linear: bias must have N entries")
+        bias = (bias if bias.dtype == torch.float32 else bias.float()).contiguous()
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    elif out.dtype != torch.bfloat16 or out.numel() != M * N or not out.is_contiguous():
+        raise RuntimeError("linear: out must be a contiguous bf16 tensor of M*N elements")
+    if M > 0:
+        _check(lib().uvb_linear_bf16(_ptr(x2), _ptr(weight), _ptr(bias), _ptr(out), M, N, K, x2.stride(0),
+                                     weight.stride(0), N, int(act), _stream(x)))
+        launch_count += 1
+    return out.view(*x.shape[:-1], N)

@@ -113,50 +113,107 @@ int make_matrix_map(CUtensorMap* tm, const void* base, int rows, int cols, int64
   return UVB_OK;
 }
 
-template <int kCtas>
+template <int kCtas, int kBN>
 int launch_gemm(uvb::GemmParams& p, const void* x, const void* w, void* y, int64_t ldx, int64_t ldw, int64_t ldy,
-                int sms, cudaStream_t stream) {
-  using SM = uvb::GemmSmem<kCtas>;
+                int workers, cudaStream_t stream) {
+  using SM = uvb::GemmSmem<kCtas, kBN>;
   int rc;
   if ((rc = make_matrix_map(&p.tm_a, x, p.M, p.K, ldx, uvb::kGemmBM)) != UVB_OK) return rc;
-  if ((rc = make_matrix_map(&p.tm_b, w, p.N, p.K, ldw, uvb::kGemmBN / kCtas)) != UVB_OK) return rc;
+  if ((rc = make_matrix_map(&p.tm_b, w, p.N, p.K, ldw, kBN / kCtas)) != UVB_OK) return rc;
   if ((rc = make_matrix_map(&p.tm_c, y, p.M, p.N, ldy, uvb::kGemmBM)) != UVB_OK) return rc;
   p.n_m = (p.M + uvb::kGemmBM * kCtas - 1) / (uvb::kGemmBM * kCtas);
-  p.n_n = (p.N + uvb::kGemmBN - 1) / uvb::kGemmBN;
+  p.n_n = (p.N + kBN - 1) / kBN;
   const long long tiles = static_cast<long long>(p.n_m) * p.n_n;
   if (tiles > 0x7fffffffLL) return fail(UVB_ERR_INVALID, "too many output tiles");
-  auto kern = uvb::gemm_bf16_kernel<kCtas>;
-  UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+  // Rasterisation: the slab of B a group of column tiles covers (group_n x kBN x K bf16) should stay in the
+  // 126 MB L2 while the row tiles stream past, so A is read from DRAM once per group: as few groups as an
+  // 80 MB slab budget allows, all of the same width.
+  const double slab_tile = static_cast<double>(kBN) * p.K * 2.0;
+  int fit = static_cast<int>(80e6 / slab_tile);
+  if (fit < 1) fit = 1;
+  const int groups = (p.n_n + fit - 1) / fit;
+  p.group_n = (p.n_n + groups - 1) / groups;
+  auto kern = uvb::gemm_bf16_kernel<kCtas, kBN>;
+  static int attr_dev = -1;         // per instantiation: the attribute is set once per device
+  int dev = 0;
+  UVB_CUDA(cudaGetDevice(&dev));
+  if (dev != attr_dev) {
+    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+    attr_dev = dev;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(uvb::kGemmThreads);
   cfg.dynamicSmemBytes = SM::kDynBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  long long workers = sms / kCtas;
   if (kCtas == 2) {
-    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // persistent pairs: no more clusters than can be resident at once (one per TPC)
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
-      int n = 0;
-      UVB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      max_clusters = n;
-    }
-    if (max_clusters <= 0) return fail(UVB_ERR_UNSUPPORTED, "no CTA pair of the GEMM kernel fits on this device");
-    if (workers > max_clusters) workers = max_clusters;
   }
-  if (workers > tiles) workers = tiles;
-  cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtas));
+  long long n = workers;
+  if (n > tiles) n = tiles;
+  cfg.gridDim = dim3(static_cast<unsigned>(n * kCtas));
   UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return UVB_OK;
+}
+
+// persistent workers (CTAs or CTA pairs) the device can hold at once
+template <int kCtas>
+int gemm_workers(int sms, int* out) {
+  if (kCtas == 1) {
+    *out = sms;
+    return UVB_OK;
+  }
+  static int cached_dev = -1, cached = 0;
+  int dev = 0;
+  UVB_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    using SM = uvb::GemmSmem<2, 256>;
+    auto kern = uvb::gemm_bf16_kernel<2, 256>;
+    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(uvb::kGemmThreads);
+    cfg.dynamicSmemBytes = SM::kDynBytes;
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    UVB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));      // one pair per TPC
+    if (n <= 0) return fail(UVB_ERR_UNSUPPORTED, "no CTA pair of the GEMM kernel fits on this device");
+    cached = n < sms / 2 ? n : sms / 2;
+    cached_dev = dev;
+  }
+  *out = cached;
+  return UVB_OK;
+}
+
+// Tile width: the persistent grid runs ceil(tiles / workers) waves; 192-wide tiles cost ~3 % more per flop
+// (less operand reuse) but often fill the last wave better (N = 1536: 10.4 -> 13.8 waves).
+template <int kCtas>
+int pick_tile_n(const uvb::GemmParams& p, int workers) {
+  static const int forced = [] {
+    const char* e = getenv("UVB_GEMM_BN");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced == 192 || forced == 256) return forced;
+  const long long n_m = (p.M + uvb::kGemmBM * kCtas - 1) / (uvb::kGemmBM * kCtas);
+  auto cost = [&](int bn, double penalty) {
+    const long long tiles = n_m * ((p.N + bn - 1) / bn);
+    const long long waves = (tiles + workers - 1) / workers;
+    return static_cast<double>(waves) * bn * penalty;
+  };
+  return cost(192, 1.03) < cost(256, 1.0) ? 192 : 256;
 }
 
 unsigned long long* g_timeline = nullptr;   // diagnostics: see uvb_debug_fmha_timeline
@@ -335,7 +392,7 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 103; }
+int uvb_version(void) { return 104; }
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -628,13 +685,22 @@ int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, in
   p.N = N;
   p.K = K;
   p.act = act;
-  // Tuning hook (read once): UVB_GEMM_CTAS=1 keeps one CTA per tile instead of CTA pairs (cta_group::2)
+  // Tuning hooks (read once): UVB_GEMM_CTAS=1 keeps one CTA per tile instead of CTA pairs (cta_group::2);
+  // UVB_GEMM_BN=192|256 pins the tile width
   static const int ctas = [] {
     const char* e = getenv("UVB_GEMM_CTAS");
     return e != nullptr && atoi(e) == 1 ? 1 : 2;
   }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return ctas == 2 ? launch_gemm<2>(p, x, w, y, ldx, ldw, ldy, sms, st) : launch_gemm<1>(p, x, w, y, ldx, ldw, ldy, sms, st);
+  int workers = 0;
+  if (ctas == 2) {
+    if ((rc = gemm_workers<2>(sms, &workers)) != UVB_OK) return rc;
+    return pick_tile_n<2>(p, workers) == 192 ? launch_gemm<2, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)
+                                             : launch_gemm<2, 256>(p, x, w, y, ldx, ldw, ldy, workers, st);
+  }
+  if ((rc = gemm_workers<1>(sms, &workers)) != UVB_OK) return rc;
+  return pick_tile_n<1>(p, workers) == 192 ? launch_gemm<1, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)
+                                           : launch_gemm<1, 256>(p, x, w, y, ldx, ldw, ldy, workers, st);
 }
 
 }  // extern "C"

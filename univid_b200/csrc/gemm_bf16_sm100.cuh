@@ -7,13 +7,15 @@
 //   warp 0      TMA producer: A panel [128 rows x 64 k] and B panel [256/kCtas rows x 64 k] per ring stage
 //   warp 1      tcgen05.mma issuer (one elected lane; in a pair only the leader CTA issues) + TMEM allocator
 //   warps 2-5   epilogue: TMEM -> registers -> (+bias, round, GELU) -> swizzled smem panel -> TMA store
-// Output tile per CTA is 128 x 256 (a pair computes 256 x 256: each CTA holds its 128 rows of A and HALF of the
-// B tile, the tensor cores of both SMs read both halves -- half the shared-memory operand traffic per flop).
-// TMEM holds two 128 x 256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the MMAs of tile
-// i+1.  Shared memory: kStages x (A 16 KiB + B 32/kCtas KiB) ring, two 16 KiB output staging panels.
-// Tiles are dealt round-robin to the persistent CTAs in an order that walks 8 column tiles (2048 outputs) for
-// each row tile before moving down, so the CTAs running at one time share A rows and a B slab that fits in L2.
-// Ragged M / N / K edges are handled by TMA (zero fill on load, clipping on store).
+// Output tile per CTA is 128 x kBN, kBN = 256 or 192 (a pair computes 256 x kBN: each CTA holds its 128 rows of A
+// and HALF of the B tile, the tensor cores of both SMs read both halves -- half the shared-memory operand traffic
+// per flop).  The host picks kBN per problem so that the number of tiles fills whole waves of the persistent grid
+// (N = 1536 on 74 pairs: 10.4 waves of 256-wide tiles, 13.8 of 192-wide ones).  TMEM holds two 128 x kBN fp32
+// accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  Shared memory: kStages x (A 16 KiB +
+// B kBN/kCtas x 128 B) ring, two 16 KiB output staging panels.
+// Tiles are dealt round-robin to the persistent CTAs in an order that walks `group_n` column tiles for each row
+// tile before moving down; the host sizes the group so that its slab of B (group_n x kBN x K) stays in L2 while
+// A streams past once per group.  Ragged M / N / K edges are handled by TMA (zero fill on load, clipping on store).
 //
 // Rounding points follow the reference chain Linear(bf16 autocast) -> GELU: the biased accumulator is rounded to
 // bf16 first (the Linear's output), GELU is evaluated in fp32 on that value and rounded again.
@@ -23,23 +25,23 @@
 namespace uvb {
 
 constexpr int kGemmBM = 128;            // rows per CTA tile (UMMA M per CTA)
-constexpr int kGemmBN = 256;            // columns per tile (UMMA N)
 constexpr int kGemmBK = 64;             // k per ring stage = one 128-byte swizzle panel
 constexpr int kGemmThreads = 192;
-constexpr int kGemmGroupN = 8;          // column tiles walked per row tile (rasterisation)
 constexpr int kGemmPanelBytes = kGemmBM * 128;   // 16 KiB: 128 rows x 64 bf16
 
 enum GemmAct { kActNone = 0, kActGeluTanh = 1 };
 
-template <int kCtas>
+template <int kCtas, int kBN>
 struct GemmSmem {
-  static constexpr int kStages = kCtas == 2 ? 6 : 4;
+  static_assert(kBN % 64 == 0 && kBN <= 256 && (kBN / kCtas) % 16 == 0, "tile width");
   static constexpr int kABytes = kGemmPanelBytes;
-  static constexpr int kBBytes = (kGemmBN / kCtas) * 128;
+  static constexpr int kBBytes = (kBN / kCtas) * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kFixedBytes = 2 * kGemmPanelBytes + 256 * 4 + 256 + 1024;   // staging, bias, barriers, slack
+  static constexpr int kStages = (232448 - kFixedBytes) / kStageBytes < 8 ? (232448 - kFixedBytes) / kStageBytes : 8;
   static constexpr int kCOff = kStages * kStageBytes;            // 2 output staging panels
   static constexpr int kBiasOff = kCOff + 2 * kGemmPanelBytes;   // 256 fp32: bias of the current column tile
-  static constexpr int kBarOff = kBiasOff + kGemmBN * 4;
+  static constexpr int kBarOff = kBiasOff + 256 * 4;
   // barriers: full[S] empty[S] tmem_full[2] tmem_empty[2] + tmem ptr
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
@@ -48,13 +50,14 @@ struct GemmSmem {
 
 struct GemmParams {
   CUtensorMap tm_a;   // x  : dims (K, M), box (64, 128),        SWIZZLE_128B
-  CUtensorMap tm_b;   // w  : dims (K, N), box (64, 256/kCtas),  SWIZZLE_128B
+  CUtensorMap tm_b;   // w  : dims (K, N), box (64, kBN/kCtas),  SWIZZLE_128B
   CUtensorMap tm_c;   // y  : dims (N, M), box (64, 128),        SWIZZLE_128B
   const float* bias;  // [N] or nullptr
   int M, N, K;
   int act;
   int n_m;            // row tiles of (128 * kCtas) rows
-  int n_n;            // column tiles of 256
+  int n_n;            // column tiles of kBN
+  int group_n;        // column tiles walked per row tile (rasterisation)
 };
 
 // ---- 2-D TMA and cluster helpers local to the GEMM ----
@@ -147,14 +150,14 @@ __device__ __forceinline__ void gemm_commit(uint64_t* bar) {
   }
 }
 
-// tile index -> (row tile, column tile): groups of kGemmGroupN column tiles, row-major inside a group
-__device__ __forceinline__ void gemm_tile_coords(int t, int n_m, int n_n, int& tm, int& tn) {
-  const int per_group = n_m * kGemmGroupN;
+// tile index -> (row tile, column tile): groups of group_n column tiles, row-major inside a group
+__device__ __forceinline__ void gemm_tile_coords(int t, int n_m, int n_n, int group_n, int& tm, int& tn) {
+  const int per_group = n_m * group_n;
   const int g = t / per_group;
   const int r = t - g * per_group;
-  const int w = min(kGemmGroupN, n_n - g * kGemmGroupN);
+  const int w = min(group_n, n_n - g * group_n);
   tm = r / w;
-  tn = g * kGemmGroupN + (r - tm * w);
+  tn = g * group_n + (r - tm * w);
 }
 
 __device__ __forceinline__ float gelu_tanh_f32(float u) {
@@ -164,9 +167,9 @@ __device__ __forceinline__ float gelu_tanh_f32(float u) {
   return __fdividef(u, 1.0f + e);
 }
 
-template <int kCtas>
+template <int kCtas, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
-  using SM = GemmSmem<kCtas>;
+  using SM = GemmSmem<kCtas, kBN>;
   constexpr int kStages = SM::kStages;
   static_assert(SM::kDynBytes <= 232448, "shared memory budget (227 KiB)");
   extern __shared__ uint8_t smem_raw[];
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     const uint32_t full0 = kCtas == 2 ? map_to_cta(&full[0], 0) : 0u;   // leader's full[0], cluster address
     for (int t = worker; t < n_tiles; t += n_workers) {
       int tm, tn;
-      gemm_tile_coords(t, p.n_m, p.n_n, tm, tn);
+      gemm_tile_coords(t, p.n_m, p.n_n, p.group_n, tm, tn);
       const int row0 = (tm * kCtas + static_cast<int>(cta_rank)) * kGemmBM;
-      const int col0 = tn * kGemmBN + static_cast<int>(cta_rank) * (kGemmBN / kCtas);
+      const int col0 = tn * kBN + static_cast<int>(cta_rank) * (kBN / kCtas);
       for (int kb = 0; kb < n_kb; ++kb, ++ring) {
         const int stage = ring % kStages;
         mbar_wait(&empty[stage], ((ring / kStages) & 1) ^ 1);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   } else if (warp == 1) {
     // ========================================= MMA issuer ===========================================
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * kCtas, kGemmBN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * kCtas, kBN, 0, 0);
       const uint64_t a_desc = umma_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t b_desc = umma_desc_sw128(smem_u32(smem + SM::kABytes), 16, 1024);
       int ring = 0, it = 0;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         const int buf = it & 1;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + buf * kGemmBN;
+        const uint32_t d = tmem_base + buf * 256;
         for (int kb = 0; kb < n_kb; ++kb, ++ring) {
           const int stage = ring % kStages;
           mbar_wait(&full[stage], (ring / kStages) & 1);
@@ -285,26 +288,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     const uint32_t te0 = kCtas == 2 ? map_to_cta(&tmem_empty[0], 0) : 0u;
     const bool gelu = p.act == kActGeluTanh;
     int it = 0;
+    int slot = 0;                                  // staging panels used so far (they alternate)
     for (int t = worker; t < n_tiles; t += n_workers, ++it) {
       int tm, tn;
-      gemm_tile_coords(t, p.n_m, p.n_n, tm, tn);
+      gemm_tile_coords(t, p.n_m, p.n_n, p.group_n, tm, tn);
       const int row0 = (tm * kCtas + static_cast<int>(cta_rank)) * kGemmBM;
-      const int col0 = tn * kGemmBN;
+      const int col0 = tn * kBN;
       const int buf = it & 1;
       // every epilogue thread passed the last barrier of the previous tile after its last bias read
       float* sbias = smem_bias;
-      for (int c = et; c < kGemmBN; c += 128) {
+      for (int c = et; c < kBN; c += 128) {
         const int n = col0 + c;
         sbias[c] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
       }
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + lane_addr + buf * kGemmBN;
+      const uint32_t tacc = tmem_base + lane_addr + buf * 256;
 #pragma unroll 1
-      for (int j = 0; j < kGemmBN / 64; ++j) {       // 64 output columns = one staging panel
-        uint8_t* panel = smem_c + (j & 1) * kGemmPanelBytes;
-        // the TMA store that last read this panel (two panels ago) must be done reading: thread 0 waits, the
-        // barrier publishes it (it also orders the bias writes of this tile before their first use)
+      for (int j = 0; j < kBN / 64; ++j, ++slot) {   // 64 output columns = one staging panel
+        uint8_t* panel = smem_c + (slot & 1) * kGemmPanelBytes;
+        // the TMA store that last read this panel (two slots ago) must be done reading: thread 0 waits (every slot
+        // commits exactly one bulk group, empty or not), the barrier publishes it (it also orders the bias writes
+        // of this tile before their first use)
         if (et == 0) tma_store_wait_read1();
         named_bar_sync(1, 128);
         if (col0 + j * 64 < p.N) {
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             }
           }
         }
-        if (j == kGemmBN / 64 - 1) {
+        if (j == kBN / 64 - 1) {
           // accumulator fully read: hand the TMEM buffer back to the MMA issuer
           tc_fence_before();
           __syncwarp();
@@ -350,8 +355,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        if (et == 0 && col0 + j * 64 < p.N && row0 < p.M) {
-          tma_store_2d(&p.tm_c, panel, col0 + j * 64, row0);
+        if (et == 0) {
+          if (col0 + j * 64 < p.N && row0 < p.M) tma_store_2d(&p.tm_c, panel, col0 + j * 64, row0);
           tma_store_commit();
         }
       }

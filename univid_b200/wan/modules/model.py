@@ -13,6 +13,8 @@ keeps the reference's parameter names so reference checkpoints load, and its mod
 so the product's monkey patches (Wan22ContextWrapper, sp_attn_forward, LoRA targets) keep working.
 """
 import math
+import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -125,6 +127,70 @@ def _proj_for_kernel(t):
     return t.contiguous()
 
 
+# ----------------------------------------------------------------------------------------------------------
+# nn.Linear through the tcgen05 GEMM.  The attention modules keep their nn.Linear
+# children (checkpoint keys, LoRA wrappers, sp_attn_forward all rely on them); `_lin(mod, x)` computes
+# mod(x) with uvb_linear_bf16 when `mod` is a plain nn.Linear running the product's inference configuration
+# (CUDA, bf16 autocast or bf16 parameters, no autograd) and calls the module otherwise -- a wrapped or
+# trainable projection keeps the semantics its owner gave it.  UVB_LINEAR=0 routes everything through the
+# modules (A/B against cuBLAS).
+# ----------------------------------------------------------------------------------------------------------
+_USE_GEMM = os.environ.get('UVB_LINEAR', '1') != '0'
+_LINEAR_CACHE = {}
+
+
+def _linear_operands(mod):
+    """(weight bf16 [N, K], bias fp32 [N] holding bf16-rounded values | None) of an nn.Linear, cached until the
+    parameters change: autocast casts weight AND bias to bf16 on every call (the reference pays that cast per
+    autocast region); here the copy is made once per parameter version."""
+    w, b = mod.weight, mod.bias
+    key = id(w)
+    ver = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+    hit = _LINEAR_CACHE.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == ver:
+        return hit[2], hit[3]
+    with torch.no_grad():
+        wb = w.detach() if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
+        bb = None if b is None else b.detach().to(torch.bfloat16).float()
+    if len(_LINEAR_CACHE) > 4096:
+        for k in [k for k, v in _LINEAR_CACHE.items() if v[0]() is None]:
+            del _LINEAR_CACHE[k]
+    _LINEAR_CACHE[key] = (weakref.ref(w), ver, wb, bb)
+    return wb, bb
+
+
+def _gemm_ok(mod, x):
+    if not (_USE_GEMM and type(mod) is nn.Linear and x.is_cuda and mod.weight.is_cuda):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or mod.weight.requires_grad
+                                    or (mod.bias is not None and mod.bias.requires_grad)):
+        return False
+    if mod.in_features % 8 != 0 or mod.out_features % 8 != 0 or x.dtype not in (torch.bfloat16, torch.float32):
+        return False
+    if torch.is_autocast_enabled('cuda'):
+        return torch.get_autocast_dtype('cuda') == torch.bfloat16
+    return mod.weight.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+
+
+def _lin(mod, x, act=_ext.ACT_NONE):
+    """mod(x) for a projection module (optionally followed by tanh-GELU when act is set: the caller has
+    checked that the activation module is nn.GELU(approximate='tanh'))."""
+    if _gemm_ok(mod, x):
+        w, b = _linear_operands(mod)
+        return _ext.linear(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), w, b, act=act)
+    y = mod(x)
+    return y if act == _ext.ACT_NONE else nn.functional.gelu(y, approximate='tanh')
+
+
+def _ffn_forward(ffn, h):
+    """block.ffn(h): Linear -> GELU(tanh) -> Linear with the activation fused into the first GEMM's epilogue when
+    the container has exactly the reference's structure (model.py:212-214)."""
+    if (isinstance(ffn, nn.Sequential) and len(ffn) == 3 and type(ffn[1]) is nn.GELU and ffn[1].approximate == 'tanh'
+            and _gemm_ok(ffn[0], h) and _gemm_ok(ffn[2], h)):
+        return _lin(ffn[2], _lin(ffn[0], h, act=_ext.ACT_GELU_TANH))
+    return ffn(h)
+
+
 class WanSelfAttention(nn.Module):
 
     def __init__(self,
@@ -172,7 +238,7 @@ class WanSelfAttention(nn.Module):
             w = getattr(self.o, 'weight', None)
             if w is not None and w.dtype != x.dtype:
                 x = x.to(w.dtype)
-        return self.o(x)
+        return _lin(self.o, x)
 
     def forward(self, x, seq_lens, grid_sizes, freqs):
         r"""
@@ -185,8 +251,8 @@ class WanSelfAttention(nn.Module):
         if tuple(self.window_size) != (-1, -1):
             raise NotImplementedError('univid_b200: sliding-window self-attention is not implemented')
         b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
-        q, k = self._prologue(self.q(x), self.k(x), _cos_sin_table(freqs, x.device), grid_sizes)
-        v = self.v(x).view(b, s, n, d)
+        q, k = self._prologue(_lin(self.q, x), _lin(self.k, x), _cos_sin_table(freqs, x.device), grid_sizes)
+        v = _lin(self.v, x).view(b, s, n, d)
         if v.dtype != torch.bfloat16:
             v = v.to(torch.bfloat16)
         x = _ext.fmha_fwd(q, k, v, k_lens=_k_lens_arg(seq_lens, b, s, x.device))
@@ -210,10 +276,10 @@ class WanCrossAttention(WanSelfAttention):
         """
         b, n, d = x.size(0), self.num_heads, self.head_dim
         fused = text_weight != 1.0 and text_len > 0
-        q, _ = self._prologue(self.q(x), None, None, None)
+        q, _ = self._prologue(_lin(self.q, x), None, None, None)
         if not fused:
-            _, k = self._prologue(None, self.k(context), None, None)
-            v = self.v(context).view(b, -1, n, d)
+            _, k = self._prologue(None, _lin(self.k, context), None, None)
+            v = _lin(self.v, context).view(b, -1, n, d)
             if v.dtype != torch.bfloat16:
                 v = v.to(torch.bfloat16)
             lk = k.size(1)
@@ -225,13 +291,13 @@ class WanCrossAttention(WanSelfAttention):
         # the image of zero.
         lk = context.size(1)
         zero = context.new_zeros(1, 1, context.size(-1))
-        b_k, b_v = self.k(zero).flatten().float(), self.v(zero).flatten().float()
+        b_k, b_v = _lin(self.k, zero).flatten().float(), _lin(self.v, zero).flatten().float()
         w_vec = torch.ones(lk, dtype=torch.float32, device=x.device)
         w_vec[:text_len] = float(text_weight)
-        k_lin = (self.k(context).float() - b_k).to(torch.bfloat16)
+        k_lin = (_lin(self.k, context).float() - b_k).to(torch.bfloat16)
         # out = sum_j p_j (w_j l_j + b_v) = sum_j p_j (w_j l_j) + b_v: the weight rides on the 512 bias-free
         # value rows (one tiny elementwise op) instead of on every probability inside the attention kernel
-        v_lin = ((self.v(context).float() - b_v) * w_vec.view(1, lk, 1)).to(torch.bfloat16).view(b, lk, n, d)
+        v_lin = ((_lin(self.v, context).float() - b_v) * w_vec.view(1, lk, 1)).to(torch.bfloat16).view(b, lk, n, d)
         wk, eps_k, pre_k = _norm_weight(self.norm_k)
         if pre_k is not None:
             raise NotImplementedError('fused text weighting needs a WanRMSNorm or Identity norm_k')
@@ -316,7 +382,7 @@ class WanAttentionBlock(nn.Module):
             h = x
         c = self.cross_attn(h, context, context_lens)
         x, h = _ext.block_glue(x, y=_bf16c(c), gate=None, scale=scale_f, shift=shift_f, eps=self.norm2.eps, inplace=True)
-        y = self.ffn(h)
+        y = _ffn_forward(self.ffn, h)
         x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_f, want_h=False, inplace=True)
         return x
 
