@@ -28,6 +28,7 @@ REF_ROOT = os.environ.get("UNIVID_REFERENCE", "/root/reference")
 MODULES_DIR = os.path.join(REF_ROOT, "models/wan/utils/modules")
 DIST_DIR = os.path.join(REF_ROOT, "models/wan/distributed")
 PIPELINE = os.path.join(REF_ROOT, "models/model_pipeline.py")
+ANIMATE = os.path.join(MODULES_DIR, "animate/model_animate.py")
 
 
 def available():
@@ -121,3 +122,23 @@ def load_context_wrapper():
     exec(code, ns)
     _CACHE["wrapper"] = ns["Wan22ContextWrapper"]
     return _CACHE["wrapper"]
+
+
+def load_animate_attention():
+    """(WanAnimateSelfAttention, WanAnimateCrossAttention, namespace) of the reference, cut out of
+    models/wan/utils/modules/animate/model_animate.py by AST (the module itself imports face/motion encoders,
+    diffusers.loaders and a relative path that does not exist in the tree) and bound to the reference's own
+    WanSelfAttention / WanRMSNorm / rope_apply and the SDPA-routed flash_attention of load_modules()."""
+    if "animate" in _CACHE:
+        return _CACHE["animate"]
+    _, model = load_modules()
+    tree = ast.parse(open(ANIMATE).read())
+    want = ("WanAnimateSelfAttention", "WanAnimateCrossAttention")
+    nodes = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in want]
+    code = compile(ast.Module(body=nodes, type_ignores=[]), ANIMATE, "exec")
+    ns = {"torch": torch, "nn": nn, "WanSelfAttention": model.WanSelfAttention, "WanRMSNorm": model.WanRMSNorm,
+          "rope_apply": model.rope_apply, "flash_attention": model.flash_attention}
+    exec(code, ns)
+    # the namespace is returned too: rebinding ns["flash_attention"] switches the attention route of both classes
+    _CACHE["animate"] = (ns["WanAnimateSelfAttention"], ns["WanAnimateCrossAttention"], ns)
+    return _CACHE["animate"]

@@ -225,6 +225,36 @@ def cross_attention(x, context, prm, num_heads, context_lens=None, eps=1e-6, bf1
     return _linear(a.flatten(2), prm["o.weight"], prm["o.bias"], bf16)
 
 
+def animate_cross_attention(x, context, prm, num_heads, context_lens=None, eps=1e-6, bf16=True,
+                            route="sdpa", use_img_emb=True, img_tokens=257):
+    """WanAnimateCrossAttention.forward (models/wan/utils/modules/animate/model_animate.py:111-146): the first 257
+    context rows are CLIP image tokens with their own k_img / v_img / norm_k_img (:103-106, :117-119, :129-132); the
+    same queries attend to the image keys (all of them, k_lens=None) and to the text keys (k_lens=context_lens),
+    the two results are added in the attention output dtype (:141-144) and projected by `o`.  Under the SDPA route
+    both results are bf16 and so is their sum; under the flash route they are fp32 (attention.py:130)."""
+    b = x.size(0)
+    d = x.shape[2] // num_heads
+    cd = torch.bfloat16 if bf16 else torch.float32
+
+    def attend(q, k, v, lens):
+        if route == "sdpa":
+            return attention_sdpa(q, k, v, dtype=cd)
+        return attention_varlen(q, k, v, k_lens=lens, compute_dtype=cd)
+
+    if use_img_emb:
+        context_img, context = context[:, :img_tokens], context[:, img_tokens:]
+    q = rms_norm(_linear(x, prm["q.weight"], prm["q.bias"], bf16), prm["norm_q.weight"], eps).view(b, -1, num_heads, d)
+    k = rms_norm(_linear(context, prm["k.weight"], prm["k.bias"], bf16), prm["norm_k.weight"], eps).view(b, -1, num_heads, d)
+    v = _linear(context, prm["v.weight"], prm["v.bias"], bf16).view(b, -1, num_heads, d)
+    a = attend(q, k, v, context_lens).flatten(2)
+    if use_img_emb:
+        k_img = rms_norm(_linear(context_img, prm["k_img.weight"], prm["k_img.bias"], bf16),
+                         prm["norm_k_img.weight"], eps).view(b, -1, num_heads, d)
+        v_img = _linear(context_img, prm["v_img.weight"], prm["v_img.bias"], bf16).view(b, -1, num_heads, d)
+        a = a + attend(q, k_img, v_img, None).flatten(2)
+    return _linear(a, prm["o.weight"], prm["o.bias"], bf16)
+
+
 # ------------------------------------------------------------------------------------------------
 # WanLayerNorm -- model.py:88-98 ; WanAttentionBlock -- model.py:183-259
 # ------------------------------------------------------------------------------------------------
