@@ -194,6 +194,32 @@ enum uvb_act { UVB_ACT_NONE = 0, UVB_ACT_GELU_TANH = 1 };
 int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
                     int64_t ldw, int64_t ldy, int act, void* stream);
 
+/* Sampler update between two DiT forwards, one fused elementwise pass.
+ * Replaces: the classifier-free-guidance combine `uncond + g * (cond - uncond)` (models/wan/textimage2video.py:385-386)
+ * and FlowUniPCMultistepScheduler.step (models/wan/utils/fm_solvers_unipc.py:657-741: convert_model_output :320-323,
+ * UniC corrector :549-628, UniP predictor :395-486) for solver_order <= 2, predict_x0, flow_prediction.
+ * The host computes the scalar coefficients in the reference's fp32 arithmetic (uvb_unipc_coef); the kernel applies
+ *   v    = uncond ? uncond + guide * (cond - uncond) : cond
+ *   m_t  = x - sigma * v
+ *   x_c  = corrector_order ? c_a * last - c_b * m0 - c_ab * ([c_rho0 * (m1 - m0) / c_rk +] c_rho_last * (m_t - m0)) : x
+ *   next = p_a * x_c - p_b * m_t [- p_ab * (p_rho0 * (m0 - m_t) / p_rk)]          (bracket: order 2)
+ * with every operation individually rounded (bit-identical to the fp32 reference chain).
+ *   cond, uncond (or NULL), x, last, m0, m1: DEVICE fp32 [n], 16-byte aligned; last/m0/m1 may be NULL when the orders
+ *   do not need them.  m_out, xc_out, x_next: DEVICE fp32 [n] outputs (must not alias the inputs of later steps the
+ *   caller still needs).  coef: HOST pointer.
+ */
+typedef struct uvb_unipc_coef {
+  float guide_scale;
+  float sigma;
+  int32_t corrector_order;   /* 0 = no corrector, 1 or 2 */
+  float c_a, c_b, c_ab, c_rk, c_rho0, c_rho_last;
+  int32_t predictor_order;   /* 1 or 2 */
+  float p_a, p_b, p_ab, p_rk, p_rho0;
+} uvb_unipc_coef;
+int uvb_unipc_step(const float* cond, const float* uncond, const float* x, const float* last, const float* m0,
+                   const float* m1, float* m_out, float* xc_out, float* x_next, int64_t n,
+                   const uvb_unipc_coef* coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ MODULES_DIR = os.path.join(REF_ROOT, "models/wan/utils/modules")
 DIST_DIR = os.path.join(REF_ROOT, "models/wan/distributed")
 PIPELINE = os.path.join(REF_ROOT, "models/model_pipeline.py")
 ANIMATE = os.path.join(MODULES_DIR, "animate/model_animate.py")
+UNIPC = os.path.join(REF_ROOT, "models/wan/utils/fm_solvers_unipc.py")
 
 
 def available():
@@ -142,3 +143,71 @@ def load_animate_attention():
     # the namespace is returned too: rebinding ns["flash_attention"] switches the attention route of both classes
     _CACHE["animate"] = (ns["WanAnimateSelfAttention"], ns["WanAnimateCrossAttention"], ns)
     return _CACHE["animate"]
+
+
+def load_unipc_scheduler():
+    """The reference's FlowUniPCMultistepScheduler (models/wan/utils/fm_solvers_unipc.py), loaded unmodified.  The
+    `diffusers` names it imports are stood in for by the minimum that gives them their documented behaviour:
+    `register_to_config` records the constructor arguments (defaults included) in `self.config`,
+    `ConfigMixin.register_to_config(**kw)` updates it, SchedulerOutput carries `prev_sample`."""
+    if "unipc" in _CACHE:
+        return _CACHE["unipc"]
+    import dataclasses
+    import enum
+    import functools
+    import inspect
+    _install_diffusers_stub()
+
+    class ConfigMixin:
+        def register_to_config(self, **kw):
+            if not hasattr(self, "config"):
+                self.config = types.SimpleNamespace()
+            for k, v in kw.items():
+                setattr(self.config, k, v)
+
+    def register_to_config(init):
+        sig = inspect.signature(init)
+
+        @functools.wraps(init)
+        def wrapped(self, *args, **kwargs):
+            bound = sig.bind(self, *args, **kwargs)
+            bound.apply_defaults()
+            cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+            ConfigMixin.register_to_config(self, **cfg)
+            init(self, *args, **kwargs)
+        return wrapped
+
+    class SchedulerMixin:
+        pass
+
+    @dataclasses.dataclass
+    class SchedulerOutput:
+        prev_sample: torch.Tensor
+
+    class KarrasDiffusionSchedulers(enum.Enum):
+        UniPCMultistepScheduler = 1
+
+    cu = types.ModuleType("diffusers.configuration_utils")
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    sch = types.ModuleType("diffusers.schedulers")
+    su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+    su.KarrasDiffusionSchedulers, su.SchedulerMixin, su.SchedulerOutput = KarrasDiffusionSchedulers, SchedulerMixin, SchedulerOutput
+    ut = types.ModuleType("diffusers.utils")
+    ut.deprecate = lambda *a, **k: None
+    ut.is_scipy_available = lambda: False
+    saved = {k: sys.modules.get(k) for k in ("diffusers.configuration_utils", "diffusers.schedulers",
+                                             "diffusers.schedulers.scheduling_utils", "diffusers.utils")}
+    sys.modules.update({"diffusers.configuration_utils": cu, "diffusers.schedulers": sch,
+                        "diffusers.schedulers.scheduling_utils": su, "diffusers.utils": ut})
+    try:
+        spec = importlib.util.spec_from_file_location("uvref_fm_solvers_unipc", UNIPC)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():       # the model loader's identity-decorator stub stays in place for model.py
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _CACHE["unipc"] = mod.FlowUniPCMultistepScheduler
+    return _CACHE["unipc"]

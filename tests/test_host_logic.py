@@ -178,3 +178,42 @@ def test_lin_helper_routes_cpu_and_wrapped_modules_through_the_module():
         lin.weight.mul_(3.0)
     w2, _ = mdl._linear_operands(lin)
     assert w2 is not w and torch.equal(w2, lin.weight.detach().to(torch.bfloat16))
+
+
+def test_unipc_dropin_has_the_reference_interface():
+    """Drop-in FlowUniPCMultistepScheduler: constructor / method signatures of
+    models/wan/utils/fm_solvers_unipc.py:79-97, :162-169, :657-662; schedule identical to the oracle; options the
+    fused kernel does not cover raise instead of being ignored."""
+    import torch
+    from oracle import ref_loader
+    from oracle import unipc_oracle as uo
+    mod = importlib.import_module("univid_b200.wan.utils.fm_solvers_unipc")
+    cls = mod.FlowUniPCMultistepScheduler
+    want_init = ["self", "num_train_timesteps", "solver_order", "prediction_type", "shift", "use_dynamic_shifting",
+                 "thresholding", "dynamic_thresholding_ratio", "sample_max_value", "predict_x0", "solver_type",
+                 "lower_order_final", "disable_corrector", "solver_p", "timestep_spacing", "steps_offset",
+                 "final_sigmas_type"]
+    assert list(inspect.signature(cls.__init__).parameters) == want_init
+    assert list(inspect.signature(cls.set_timesteps).parameters) == ["self", "num_inference_steps", "device", "sigmas", "mu", "shift"]
+    assert list(inspect.signature(cls.step).parameters) == ["self", "model_output", "timestep", "sample", "return_dict", "generator"]
+    if ref_loader.available():
+        ref = ref_loader.load_unipc_scheduler()
+        assert list(inspect.signature(ref.__init__).parameters) == want_init
+        assert list(inspect.signature(ref.step).parameters) == list(inspect.signature(cls.step).parameters)
+    s = cls(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(50, device="cpu", shift=5.0)
+    t, sig = uo.sampling_schedule(50, 5.0)
+    assert torch.equal(s.timesteps, t) and torch.equal(s.sigmas, sig) and s.config.solver_order == 2
+    for kw in (dict(solver_order=3), dict(thresholding=True), dict(predict_x0=False), dict(use_dynamic_shifting=True),
+               dict(prediction_type="epsilon"), dict(final_sigmas_type="sigma_min")):
+        with pytest.raises(NotImplementedError):
+            cls(**kw)
+    with pytest.raises(RuntimeError):                     # no CPU path
+        s.step(torch.zeros(1, 4), s.timesteps[0], torch.zeros(1, 4))
+    # the scalar coefficients are the oracle's, bit for bit (both mirror fm_solvers_unipc.py:395-455 / :549-606)
+    for corr, (i_t, i_s0, hist, order) in ((True, (3, 2, [1], 2)), (False, (4, 3, [2], 2)), (True, (1, 0, [], 1)),
+                                           (False, (50, 49, [], 1))):
+        a, b, ab, rk, rhos = s._bh(i_t, i_s0, hist, order, corr)
+        c = uo.bh_coefficients(s.sigmas, i_t, i_s0, hist, order, "bh2", corr)
+        assert (a, b, ab) == (float(c["a"]), float(c["b"]), float(c["ab"]))
+        assert rhos == [float(r) for r in c["rhos"]] and (not hist or rk == float(c["rks"][0]))

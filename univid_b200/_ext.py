@@ -16,14 +16,23 @@ EXPORTS = (
     "uvb_fmha_fwd_bf16", "uvb_fmha_workspace_bytes", "uvb_xattn_fwd_bf16", "uvb_debug_fmha_timeline",
     "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
-    "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16",
+    "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step",
 )
-ABI_VERSION = 104
+ABI_VERSION = 105
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
 _vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 _lib = None
+
+
+class UnipcCoef(_c.Structure):
+    """uvb_unipc_coef (include/univid_b200.h)."""
+    _fields_ = [("guide_scale", _f), ("sigma", _f), ("corrector_order", _c.c_int32), ("c_a", _f), ("c_b", _f),
+                ("c_ab", _f), ("c_rk", _f), ("c_rho0", _f), ("c_rho_last", _f), ("predictor_order", _c.c_int32),
+                ("p_a", _f), ("p_b", _f), ("p_ab", _f), ("p_rk", _f), ("p_rho0", _f)]
+
+
 launch_count = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -79,6 +88,8 @@ def lib():
     L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _f, _vp]
     L.uvb_linear_bf16.restype = _i
     L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
+    L.uvb_unipc_step.restype = _i
+    L.uvb_unipc_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _c.POINTER(UnipcCoef), _vp]
     if L.uvb_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB_PATH} has ABI version {L.uvb_version()}, expected {ABI_VERSION}: rebuild it "
                            "with `python -m univid_b200.build --force`")
@@ -435,3 +446,24 @@ def linear(x, weight, bias=None, act=ACT_NONE, out=None):
                                      weight.stride(0), N, int(act), _stream(x)))
         launch_count += 1
     return out.view(*x.shape[:-1], N)
+
+
+def unipc_step(cond, uncond, x, last, m0, m1, coef):
+    """Fused CFG combine + UniPC step (uvb_unipc_step).  All tensors fp32 CUDA with x's number of elements; coef is
+    a UnipcCoef.  Returns (m_t, x_corrected, x_next) as new tensors shaped like x."""
+    global launch_count
+    _require_cuda(cond, uncond, x, last, m0, m1)
+    _no_grad_only(cond, uncond, x)
+    n = x.numel()
+    ins = []
+    for t in (cond, uncond, x, last, m0, m1):
+        if t is None:
+            ins.append(None)
+            continue
+        if t.dtype != torch.float32 or t.numel() != n:
+            raise RuntimeError("unipc_step: every tensor must be fp32 with the sample's number of elements")
+        ins.append(t.contiguous())
+    m_t, x_c, x_n = torch.empty_like(ins[2]), torch.empty_like(ins[2]), torch.empty_like(ins[2])
+    _check(lib().uvb_unipc_step(*[_ptr(t) for t in ins], _ptr(m_t), _ptr(x_c), _ptr(x_n), n, _c.byref(coef), _stream(x)))
+    launch_count += 1
+    return m_t, x_c, x_n

@@ -10,6 +10,7 @@
 #include "qk_norm_rope.cuh"
 #include "block_glue.cuh"
 #include "gemm_bf16_sm100.cuh"
+#include "sampler_step.cuh"
 
 namespace {
 
@@ -392,7 +393,7 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 104; }
+int uvb_version(void) { return 105; }
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -701,6 +702,62 @@ int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, in
   if ((rc = gemm_workers<1>(sms, &workers)) != UVB_OK) return rc;
   return pick_tile_n<1>(p, workers) == 192 ? launch_gemm<1, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)
                                            : launch_gemm<1, 256>(p, x, w, y, ldx, ldw, ldy, workers, st);
+}
+
+int uvb_unipc_step(const float* cond, const float* uncond, const float* x, const float* last, const float* m0,
+                   const float* m1, float* m_out, float* xc_out, float* x_next, int64_t n,
+                   const uvb_unipc_coef* coef, void* stream) {
+  if (cond == nullptr || x == nullptr || m_out == nullptr || xc_out == nullptr || x_next == nullptr || coef == nullptr)
+    return fail(UVB_ERR_INVALID, "null pointer");
+  if (n <= 0) return fail(UVB_ERR_INVALID, "bad element count %lld", static_cast<long long>(n));
+  if (coef->corrector_order < 0 || coef->corrector_order > 2 || coef->predictor_order < 1 || coef->predictor_order > 2)
+    return fail(UVB_ERR_UNSUPPORTED, "UniPC orders (corrector %d, predictor %d) beyond solver_order 2",
+                coef->corrector_order, coef->predictor_order);
+  if (coef->corrector_order > 0 && (last == nullptr || m0 == nullptr)) return fail(UVB_ERR_INVALID, "corrector needs last and m0");
+  if (coef->corrector_order == 2 && m1 == nullptr) return fail(UVB_ERR_INVALID, "second-order corrector needs m1");
+  if (coef->predictor_order == 2 && m0 == nullptr) return fail(UVB_ERR_INVALID, "second-order predictor needs m0");
+  for (const void* q : {static_cast<const void*>(cond), static_cast<const void*>(uncond), static_cast<const void*>(x),
+                        static_cast<const void*>(last), static_cast<const void*>(m0), static_cast<const void*>(m1),
+                        static_cast<const void*>(m_out), static_cast<const void*>(xc_out), static_cast<const void*>(x_next)}) {
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return fail(UVB_ERR_INVALID, "pointers must be 16-byte aligned");
+  }
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+  int sms = 0;
+  if ((rc = sm_count(&sms)) != UVB_OK) return rc;
+  uvb::SamplerStepParams p;
+  memset(&p, 0, sizeof(p));
+  p.cond = cond;
+  p.uncond = uncond;
+  p.x = x;
+  p.last = last;
+  p.m0 = m0;
+  p.m1 = m1;
+  p.m_out = m_out;
+  p.xc_out = xc_out;
+  p.x_next = x_next;
+  p.n = n;
+  p.guide = coef->guide_scale;
+  p.sigma = coef->sigma;
+  p.corr_order = coef->corrector_order;
+  p.c_a = coef->c_a;
+  p.c_b = coef->c_b;
+  p.c_ab = coef->c_ab;
+  p.c_rk = coef->c_rk;
+  p.c_rho0 = coef->c_rho0;
+  p.c_rho_last = coef->c_rho_last;
+  p.pred_order = coef->predictor_order;
+  p.p_a = coef->p_a;
+  p.p_b = coef->p_b;
+  p.p_ab = coef->p_ab;
+  p.p_rk = coef->p_rk;
+  p.p_rho0 = coef->p_rho0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8LL * sms) blocks = 8LL * sms;       // grid-stride: a whole number of CTAs per SM
+  uvb::sampler_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVB_CUDA(cudaGetLastError());
+  return UVB_OK;
 }
 
 }  // extern "C"
