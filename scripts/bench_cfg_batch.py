@@ -1,0 +1,82 @@
+"""One sampler step of the 1.3B config at 32 760 tokens: the two B = 1 DiT forwards of the reference loop
+(textimage2video.py:380-383) against ONE B = 2 forward (wan/textimage2video.py::cfg_batched_forward), plus the fused
+CFG + UniPC update kernel against its eager expression.  Run under gpurun:
+    python scripts/bench_cfg_batch.py > gpurun_out/cfg_batch.log"""
+import importlib
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+mdl = importlib.import_module("univid_b200.wan.modules.model")
+t2v = importlib.import_module("univid_b200.wan.textimage2video")
+sched_mod = importlib.import_module("univid_b200.wan.utils.fm_solvers_unipc")
+
+
+def timed(fn, n):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    cfg = bench.CONFIGS["1.3B"]
+    dev = torch.device("cuda")
+    f, h, w = cfg["grid"]
+    L = f * h * w
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = mdl.WanModel(model_type="t2v", dim=cfg["dim"], ffn_dim=cfg["ffn"], num_heads=cfg["heads"],
+                             num_layers=cfg["layers"], text_len=cfg["text_len"], in_dim=16, out_dim=16).eval()
+    g = torch.Generator(device=dev).manual_seed(7)
+    lat = torch.randn(16, f, h * 2, w * 2, device=dev, generator=g)
+    ctx = torch.randn(cfg["text_len"], 4096, device=dev, generator=g)
+    ctx0 = torch.randn(300, 4096, device=dev, generator=g)
+    t = torch.tensor([500.0], device=dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        two = timed(lambda: (model([lat], t=t, context=[ctx], seq_len=L), model([lat], t=t, context=[ctx0], seq_len=L)), 2)
+        one = timed(lambda: t2v.cfg_batched_forward(model, lat, t, ctx, ctx0, L), 2)
+    print(f"two B=1 DiT forwards: {two:.2f} ms   one B=2 forward: {one:.2f} ms   ratio {one / two:.4f}")
+
+    # sampler update: fused kernel vs the eager chain (CFG combine + the scheduler's elementwise ops)
+    sch = sched_mod.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    sch.set_timesteps(50, device=dev, shift=5.0)
+    x = lat.unsqueeze(0)
+    vc, vu = torch.randn_like(x), torch.randn_like(x)
+    for k in range(3):                                      # reach the steady state (corrector + order 2)
+        x = sch.step_cfg(vc, vu, 5.0, sch.timesteps[k], x)[0]
+    state = (sch._step_index, sch.lower_order_nums, list(sch.model_outputs), sch.last_sample, sch.this_order)
+
+    def fused():
+        sch._step_index, sch.lower_order_nums, sch.model_outputs, sch.last_sample, sch.this_order = (
+            state[0], state[1], list(state[2]), state[3], state[4])
+        sch.step_cfg(vc, vu, 5.0, sch.timesteps[3], x)
+
+    m0, m1, last = state[2][-1], state[2][-2], state[3]
+
+    def eager():            # the tensor ops of one steady-state step, as the reference issues them
+        v = vu + 5.0 * (vc - vu)
+        m_t = x - 0.9 * v
+        x_t_ = 0.95 * last - 0.05 * m0
+        d1 = (m1 - m0) / -1.4
+        xc = x_t_ - 0.05 * (0.07 * d1 + 0.48 * (m_t - m0))
+        p_ = 0.95 * xc - 0.05 * m_t
+        return p_ - 0.05 * (0.5 * ((m0 - m_t) / -1.4))
+
+    fu, ea = timed(fused, 50), timed(eager, 50)
+    n = x.numel()
+    print(f"sampler update on {n} latent elements: fused (host scalars + 1 kernel) {fu * 1e3:.1f} us, eager tensor ops only "
+          f"{ea * 1e3:.1f} us; kernel traffic {36 * n / 1e6:.1f} MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,22 @@ def text_len_for(context, config):
     return min(config.bagel_sequence_length, seq_len // 2)
 
 
+class TextWeightCounter:
+    """The DiT-call counter of hooked_dit_forward (model_pipeline.py:1856-1866) on its own: `next_weight()` returns
+    the weight of the next DiT call and advances the counter.  Used by the batched-CFG denoise step, which issues the
+    conditional and the unconditional call of a sampler step as one B = 2 forward and therefore needs both weights
+    up front (wan/textimage2video.py::cfg_batched_forward)."""
+
+    def __init__(self, config=None):
+        self.config = config or TextWeightConfig()
+        self.call_index = 0
+
+    def next_weight(self):
+        w = calculate_text_weight(self.call_index, self.config)
+        self.call_index += 1
+        return w
+
+
 class FusedTextWeightSchedule:
     """Arms every WanCrossAttention of `dit_model` with the fused text weighting.
 
