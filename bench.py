@@ -401,7 +401,8 @@ def run_native_arm(args, cfg_key):
         gen = torch.Generator(device=dev).manual_seed(7)      # identical inputs on every rank
         lat = [torch.randn(16, f, h * 2, w * 2, device=dev, generator=gen)]
         ctx_in = [torch.randn(text_len, 4096, device=dev, generator=gen)]
-        tt = torch.tensor([500.0], device=dev)
+        # per-token timesteps [1, seq_len], the way the reference sampling loop calls the DiT (textimage2video.py:372-377)
+        tt = torch.full((1, L), 500.0, device=dev)
         with torch.no_grad(), torch.autocast("cuda", dtype=bf):
             model(lat, tt, ctx_in, seq_len=L)
             barrier()

@@ -152,11 +152,14 @@ int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* cons
  *                               skips the LayerNorm part (residual update only)
  *   gate / scale / shift are fp32 views into the modulation tensor (modulation + e).chunk(6): element
  *   (b, l, c) at ptr + b*mod_sb + l*mod_sl + c (element strides; mod_sl = 0 broadcasts one row per sample).
+ *   mod_index: DEVICE int32 [B*L] or NULL.  When given, token (b, l) reads modulation row mod_index[b*L + l] instead
+ *   of row l: the reference expands the timestep to one value per token (textimage2video.py:372-377, model.py:460-468)
+ *   and materialises [B, L, 6, dim]; with few distinct timesteps one row per distinct value is enough.
  *   dim in {256, 512, 1024, 1536, 2048, 3072, 4096, 5120}; all pointers 16-byte aligned.
  */
 int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x_out, const float* ln_w,
                    const float* ln_b, const float* scale, const float* shift, void* h_out, int B, int L,
-                   int dim, int64_t mod_sb, int64_t mod_sl, float eps, void* stream);
+                   int dim, int64_t mod_sb, int64_t mod_sl, const int32_t* mod_index, float eps, void* stream);
 
 /* Diagnostics: when set to a DEVICE buffer of (number of SMs) x 32 uint64, every attention launch records
  * per CTA {smid, start ns, end ns of each piece of work (up to 30)} (%globaltimer).  NULL (default) = off. */

@@ -47,6 +47,19 @@ def main():
         one = timed(lambda: t2v.cfg_batched_forward(model, lat, t, ctx, ctx0, L), 2)
     print(f"two B=1 DiT forwards: {two:.2f} ms   one B=2 forward: {one:.2f} ms   ratio {one / two:.4f}")
 
+    # per-token timesteps [1, seq_len] (textimage2video.py:372-377; ti2v: first latent frame at t = 0): one embedded row
+    # per distinct value + a row index, against the reference's materialised [1, L, 6, C] modulation
+    tt = torch.full((1, L), 500.0, device=dev)
+    tt[0, :h * w] = 0.0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        scalar = timed(lambda: model([lat], t=t, context=[ctx], seq_len=L), 2)
+        dedup = timed(lambda: model([lat], t=tt, context=[ctx], seq_len=L), 2)
+        model.max_distinct_timesteps = 0
+        expanded = timed(lambda: model([lat], t=tt, context=[ctx], seq_len=L), 2)
+        model.max_distinct_timesteps = 8
+    print(f"DiT forward: scalar t {scalar:.2f} ms   per-token t, de-duplicated rows {dedup:.2f} ms   "
+          f"per-token t, materialised [1, L, 6, C] {expanded:.2f} ms")
+
     # sampler update: fused kernel vs the eager chain (CFG combine + the scheduler's elementwise ops)
     sch = sched_mod.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
     sch.set_timesteps(50, device=dev, shift=5.0)

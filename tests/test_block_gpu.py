@@ -51,6 +51,58 @@ def test_block_glue_kernel(dim, per_tok):
     assert none is None and torch.equal(x3, want_x2 + y.float() * gate)
 
 
+@pytest.mark.parametrize("dim", [256, 1536, 3072, 5120])
+def test_block_glue_indexed_modulation_rows(dim):
+    """index [B, L] + one modulation row per distinct timestep == the materialised per-token modulation, bit for bit."""
+    from univid_b200 import _ext
+    g = torch.Generator().manual_seed(dim)
+    B, L, U = 2, 53, 3
+    x = torch.randn(B, L, dim, generator=g).cuda()
+    y = torch.randn(B, L, dim, generator=g).to(torch.bfloat16).cuda()
+    rows = (0.3 * torch.randn(1, U, 6, dim, generator=g)).cuda()
+    idx = torch.randint(0, U, (B, L), generator=g).to(torch.int32).cuda()
+    full = rows[0][idx.long()]                                   # [B, L, 6, dim]
+    for k_gate, k_scale, k_shift in ((2, 1, 0), (5, 4, 3)):
+        x1, h1 = _ext.block_glue(x, y=y, gate=rows[:, :, k_gate], scale=rows[:, :, k_scale], shift=rows[:, :, k_shift],
+                                 eps=1e-6, index=idx)
+        x2, h2 = _ext.block_glue(x, y=y, gate=full[:, :, k_gate], scale=full[:, :, k_scale], shift=full[:, :, k_shift], eps=1e-6)
+        assert torch.equal(x1, x2) and torch.equal(h1, h2)
+    with pytest.raises(RuntimeError):
+        _ext.block_glue(x, scale=rows[:, :, 1], shift=rows[:, :, 0], index=idx.long())
+
+
+def test_model_forward_with_per_token_timesteps_deduplicated():
+    """WanModel.forward with t [B, seq_len] as the reference sampling loop passes it (textimage2video.py:372-377):
+    the de-duplicated form (one embedded row per distinct timestep + a row index) against the reference's
+    materialised [B, L, 6, C] expansion (max_distinct_timesteps = 0) and, for uniform t, against the [B] form."""
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    torch.manual_seed(0)
+    model = mdl.WanModel(model_type="ti2v", dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_len=32, text_dim=64,
+                         freq_dim=64, in_dim=16, out_dim=16).cuda().eval()
+    torch.nn.init.normal_(model.head.head.weight, std=0.05)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lat = [torch.randn(16, 3, 8, 12, device="cuda", generator=g)]       # 72 tokens
+    ctx = [torch.randn(20, 64, device="cuda", generator=g)]
+    L = 80                                                                # 8 padding tokens
+    t_tok = torch.full((1, L), 640.0, device="cuda")
+    t_tok[0, :24] = 0.0                                                   # first latent frame given (ti2v): t = 0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        _, _, kw = model.embed(lat, t_tok, ctx, L)
+        assert kw["e"].shape == (1, 2, 6, 256) and kw["e_index"].shape == (1, L) and kw["e_index"].dtype == torch.int32
+        got = model(lat, t_tok, ctx, L)[0]
+        model.max_distinct_timesteps = 0
+        _, _, kw0 = model.embed(lat, t_tok, ctx, L)
+        assert kw0["e"].shape == (1, L, 6, 256) and "e_index" not in kw0
+        want = model(lat, t_tok, ctx, L)[0]
+        model.max_distinct_timesteps = 8
+        uni = model(lat, torch.full((1, L), 640.0, device="cuda"), ctx, L)[0]
+        uni_b = model(lat, torch.tensor([640.0], device="cuda"), ctx, L)[0]
+    assert torch.isfinite(got).all() and got.shape == lat[0].shape
+    assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    assert (uni - uni_b).abs().max().item() <= 2e-3 * max(1.0, uni_b.abs().max().item())
+    assert (got - uni).abs().max() > 1e-3                                  # the per-token values really matter
+
+
 @pytest.mark.parametrize("per_tok", [False, True])
 def test_block_matches_oracle(per_tok):
     """Fused block vs the oracle (bit-exactly pinned to the reference block by tests/test_block_oracle_golden.py):

@@ -217,3 +217,35 @@ def test_unipc_dropin_has_the_reference_interface():
         c = uo.bh_coefficients(s.sigmas, i_t, i_s0, hist, order, "bh2", corr)
         assert (a, b, ab) == (float(c["a"]), float(c["b"]), float(c["ab"]))
         assert rhos == [float(r) for r in c["rhos"]] and (not hist or rk == float(c["rks"][0]))
+
+
+def test_embed_deduplicates_per_token_timesteps():
+    """WanModel.embed (CPU: no kernels involved): t [B, seq_len] with few distinct values -> one embedded row per value
+    plus an int32 row index; gathering the rows reproduces the reference's materialised expansion (model.py:460-468)."""
+    import torch
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    torch.manual_seed(0)
+    model = mdl.WanModel(model_type="ti2v", dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_len=8, text_dim=32,
+                         freq_dim=32, in_dim=4, out_dim=4).eval()
+    lat = [torch.randn(4, 2, 4, 4), torch.randn(4, 2, 4, 4)]
+    ctx = [torch.randn(5, 32), torch.randn(3, 32)]
+    L = 10
+    t = torch.full((2, L), 500.0)
+    t[0, :4] = 0.0
+    t[1, :4] = 250.0
+    with torch.no_grad():
+        x, e, kw = model.embed(lat, t, ctx, L)
+        assert e.shape == (1, 3, 256) and kw["e"].shape == (1, 3, 6, 256) and kw["e_index"].dtype == torch.int32
+        model.max_distinct_timesteps = 0
+        x0, e_full, kw_full = model.embed(lat, t, ctx, L)
+        assert e_full.shape == (2, L, 256) and kw_full["e"].shape == (2, L, 6, 256) and "e_index" not in kw_full
+    idx = kw["e_index"].long()
+    assert torch.allclose(model.token_embedding(e, kw["e_index"]), e_full, atol=1e-6)
+    assert torch.allclose(kw["e"][0][idx], kw_full["e"], atol=1e-6)
+    assert torch.equal(x, x0)
+    assert model.token_embedding(e_full, None) is e_full
+    # more distinct values than the cap: the reference's expansion is kept
+    model.max_distinct_timesteps = 2
+    with torch.no_grad():
+        _, _, kw2 = model.embed(lat, t, ctx, L)
+    assert "e_index" not in kw2 and kw2["e"].shape == (2, L, 6, 256)

@@ -18,7 +18,7 @@ EXPORTS = (
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step",
 )
-ABI_VERSION = 105
+ABI_VERSION = 106
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -85,7 +85,7 @@ def lib():
     L.uvb_sp_wait.restype = _i
     L.uvb_sp_wait.argtypes = [_vp, _i, _u32, _vp]
     L.uvb_block_glue.restype = _i
-    L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _f, _vp]
+    L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _vp, _f, _vp]
     L.uvb_linear_bf16.restype = _i
     L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
     L.uvb_unipc_step.restype = _i
@@ -368,13 +368,16 @@ def sp_wait(flags_ptr, n, value, stream):
 GLUE_DIMS = (256, 512, 1024, 1536, 2048, 3072, 4096, 5120)
 
 
-def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, want_h=True, inplace=False):
+def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, want_h=True, inplace=False,
+               index=None):
     """Fused residual / LayerNorm / adaLN glue of a WanAttentionBlock (uvb_block_glue):
         x' = x + y * gate   (if y is given; a new tensor unless inplace)   h = LN(x')[* w + b] * (1 + scale) + shift -> bf16
     x fp32 [B, L, dim] contiguous; y bf16 [B, L, dim]; gate / scale / shift fp32 [B, 1 or L, dim] views with
-    unit stride over dim (chunks of the modulation tensor); ln = None | (weight, bias).  Returns (x', h)."""
+    unit stride over dim (chunks of the modulation tensor); ln = None | (weight, bias).
+    index: int32 [B, L] or None -- token (b, l) uses modulation row index[b, l]; the chunks are then [1 or B, U, dim].
+    Returns (x', h)."""
     global launch_count
-    _require_cuda(x, y, gate, scale, shift)
+    _require_cuda(x, y, gate, scale, shift, index)
     _no_grad_only(x, y, gate, scale, shift)
     B, L, dim = x.shape
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -383,15 +386,24 @@ def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, 
         raise NotImplementedError(f"block_glue: dim {dim} is not supported")
     if y is not None and (y.dtype != torch.bfloat16 or y.shape != x.shape or not y.is_contiguous()):
         raise RuntimeError("block_glue: y must be contiguous bf16 with x's shape")
+    if index is not None and (index.dtype != torch.int32 or tuple(index.shape) != (B, L) or not index.is_contiguous()):
+        raise RuntimeError("block_glue: index must be a contiguous int32 [B, L] tensor")
     sb = sl = None
     for m in (gate, scale, shift):
         if m is None:
             continue
-        if m.dtype != torch.float32 or m.dim() != 3 or m.size(0) != B or m.size(2) != dim or m.stride(2) != 1 \
-                or m.size(1) not in (1, L):
+        if m.dtype != torch.float32 or m.dim() != 3 or m.size(2) != dim or m.stride(2) != 1:
             raise RuntimeError("block_glue: modulation chunks must be fp32 [B, 1|L, dim] with unit dim stride")
-        msb = m.stride(0) if B > 1 else 0
-        msl = m.stride(1) if m.size(1) == L and L > 1 else 0
+        if index is None:
+            if m.size(0) != B or m.size(1) not in (1, L):
+                raise RuntimeError("block_glue: modulation chunks must be fp32 [B, 1|L, dim] with unit dim stride")
+            msb = m.stride(0) if B > 1 else 0
+            msl = m.stride(1) if m.size(1) == L and L > 1 else 0
+        else:
+            if m.size(0) not in (1, B):
+                raise RuntimeError("block_glue: indexed modulation chunks must be fp32 [1|B, U, dim]")
+            msb = m.stride(0) if m.size(0) > 1 else 0
+            msl = m.stride(1)
         if sb is None:
             sb, sl = msb, msl
         elif (sb, sl) != (msb, msl):
@@ -404,8 +416,8 @@ def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, 
     h = torch.empty((B, L, dim), dtype=torch.bfloat16, device=x.device) if want_h else None
     x_new = x if (y is None or inplace) else torch.empty_like(x)
     _check(lib().uvb_block_glue(_ptr(x), _ptr(y), _ptr(gate), _ptr(x_new) if y is not None else None, _ptr(lw),
-                                _ptr(lb), _ptr(scale), _ptr(shift), _ptr(h), B, L, dim, sb or 0, sl or 0, float(eps),
-                                _stream(x)))
+                                _ptr(lb), _ptr(scale), _ptr(shift), _ptr(h), B, L, dim, sb or 0, sl or 0,
+                                _ptr(index) if sb is not None else None, float(eps), _stream(x)))
     launch_count += 1
     return x_new, h
 

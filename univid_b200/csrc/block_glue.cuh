@@ -35,6 +35,8 @@ struct BlockGlueParams {
   int L;                        // rows per batch sample
   int dim;
   long long mod_sb, mod_sl;     // batch / token strides (elements) of the modulation chunks; mod_sl = 0 broadcasts
+  const int* mod_index;         // [rows] or nullptr: modulation row of each token (instead of its position l) --
+                                // per-token timesteps with few distinct values keep one row per value
   float eps;
 };
 
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(kGlueWarps * 32) block_glue_kernel(const __gri
   if (row >= p.rows) return;                               // whole groups leave together (named barriers are per group)
   const int b = static_cast<int>(row / p.L);
   const int l = static_cast<int>(row - static_cast<long long>(b) * p.L);
-  const long long mod_off = b * p.mod_sb + l * p.mod_sl;
+  const long long mod_off = b * p.mod_sb + (p.mod_index != nullptr ? __ldg(p.mod_index + row) : l) * p.mod_sl;
   const float* xr = p.x_in + row * p.dim;
 
   float x[VPL][8];

@@ -63,12 +63,14 @@ def sp_dit_forward(
     x, e, kwargs = self.embed(x, t, context, seq_len, y)
     world, rank = get_world_size(), get_rank()
     x = torch.chunk(x, world, dim=1)[rank]
-    if e.size(1) > 1:   # per-token timesteps: shard the modulation with the tokens
+    if kwargs.get('e_index') is not None:   # de-duplicated per-token timesteps: shard the row index with the tokens
+        kwargs['e_index'] = torch.chunk(kwargs['e_index'], world, dim=1)[rank].contiguous()
+    elif e.size(1) > 1:   # per-token timesteps: shard the modulation with the tokens
         e = torch.chunk(e, world, dim=1)[rank]
         kwargs['e'] = torch.chunk(kwargs['e'], world, dim=1)[rank]
     for block in self.blocks:
         x = block(x, **kwargs)
-    x = self.head(x, e)
+    x = self.head(x, self.token_embedding(e, kwargs.get('e_index')))
     x = gather_forward(x, dim=1)
     x = self.unpatchify(x, kwargs['grid_sizes'])
     return [u.float() for u in x]

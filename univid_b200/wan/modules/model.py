@@ -334,19 +334,25 @@ class WanAttentionBlock(nn.Module):
         self.ffn = nn.Sequential(nn.Linear(dim, ffn_dim), nn.GELU(approximate='tanh'), nn.Linear(ffn_dim, dim))
         self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim**0.5)
 
-    def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens):
+    def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, e_index=None):
         r"""
         x [B, L, C]; e [B, L or 1, 6, C] fp32 time modulation (a singleton token axis broadcasts, which is
         what a scalar timestep expanded over the sequence amounts to, model.py:460-468).
+        e_index: int32 [B, L] or None.  When given, e is [1, U, 6, C] -- one row per DISTINCT timestep -- and token
+        (b, l) uses row e_index[b, l] (WanModel.embed builds this form for per-token timesteps with few distinct
+        values; same values as the reference's [B, L, 6, C] expansion, never materialised).
         """
         assert e.dtype == torch.float32
         with torch.amp.autocast('cuda', dtype=torch.float32):
-            mod = self.modulation.unsqueeze(0) + e                       # fp32 [B, L or 1, 6, C]
+            mod = self.modulation.unsqueeze(0) + e                       # fp32 [B, L or 1, 6, C] ([1, U, 6, C] indexed)
+        if e_index is not None and not self._fused_glue_ok(x, mod):
+            mod = mod[0][e_index.long()]                                 # eager path: materialise [B, L, 6, C]
+            e_index = None
         shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = (mod[:, :, k] for k in range(6))
 
         if self._fused_glue_ok(x, mod):
             return self._forward_fused(x, (shift_a, scale_a, gate_a, shift_f, scale_f, gate_f), seq_lens, grid_sizes,
-                                       freqs, context, context_lens)
+                                       freqs, context, context_lens, e_index)
 
         y = self.self_attn(torch.addcmul(shift_a, self.norm1(x).float(), 1 + scale_a), seq_lens, grid_sizes, freqs)
         with torch.amp.autocast('cuda', dtype=torch.float32):
@@ -367,23 +373,25 @@ class WanAttentionBlock(nn.Module):
                 and type(self.norm3) in (WanLayerNorm, nn.Identity)
                 and not self.norm1.elementwise_affine and not self.norm2.elementwise_affine)
 
-    def _forward_fused(self, x, mods, seq_lens, grid_sizes, freqs, context, context_lens):
+    def _forward_fused(self, x, mods, seq_lens, grid_sizes, freqs, context, context_lens, e_index=None):
         """Same dataflow as above with the elementwise glue in uvb_block_glue: one pass per residual update,
         producing the next branch's bf16 input in the same pass."""
         shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = mods
         x = x.contiguous()
-        _, h = _ext.block_glue(x, scale=scale_a, shift=shift_a, eps=self.norm1.eps)
+        ix = e_index
+        _, h = _ext.block_glue(x, scale=scale_a, shift=shift_a, eps=self.norm1.eps, index=ix)
         y = self.self_attn(h, seq_lens, grid_sizes, freqs)
         if isinstance(self.norm3, WanLayerNorm):
             ln3 = (self.norm3.weight, self.norm3.bias) if self.norm3.elementwise_affine else (None, None)
-            x, h = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, ln=ln3, eps=self.norm3.eps)     # new x: the caller's is kept
+            x, h = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, ln=ln3, eps=self.norm3.eps, index=ix)   # new x: the caller's is kept
         else:
-            x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, want_h=False)
+            x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_a, want_h=False, index=ix)
             h = x
         c = self.cross_attn(h, context, context_lens)
-        x, h = _ext.block_glue(x, y=_bf16c(c), gate=None, scale=scale_f, shift=shift_f, eps=self.norm2.eps, inplace=True)
+        x, h = _ext.block_glue(x, y=_bf16c(c), gate=None, scale=scale_f, shift=shift_f, eps=self.norm2.eps, inplace=True,
+                               index=ix)
         y = _ffn_forward(self.ffn, h)
-        x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_f, want_h=False, inplace=True)
+        x, _ = _ext.block_glue(x, y=_bf16c(y), gate=gate_f, want_h=False, inplace=True, index=ix)
         return x
 
 
@@ -449,6 +457,8 @@ class WanModel(nn.Module):
         self.qk_norm = qk_norm
         self.cross_attn_norm = cross_attn_norm
         self.eps = eps
+        # per-token timesteps with at most this many distinct values are embedded once per value (0 = always expand)
+        self.max_distinct_timesteps = 8
 
         self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=patch_size, stride=patch_size)
         self.text_embedding = nn.Sequential(nn.Linear(text_dim, dim), nn.GELU(approximate='tanh'), nn.Linear(dim, dim))
@@ -492,6 +502,15 @@ class WanModel(nn.Module):
         # of materialising seq_len identical rows (the reference expands, model.py:460-461; same values)
         if t.dim() == 1:
             t = t.unsqueeze(1)
+        # Per-token timesteps [B, seq_len] (what the sampling loop passes, textimage2video.py:372-377) take only a
+        # few distinct values (t2v: one; ti2v: 0 for the given frame and t for the rest): embed each distinct value
+        # once and hand the blocks a [B, L] row index instead of a [B, L, 6, C] fp32 tensor (1.2 GB at 32 760
+        # tokens, 9.3 GB at 75 600).  torch.unique costs one host sync per DiT forward.
+        e_index = None
+        if t.size(1) > 1 and self.max_distinct_timesteps > 0:
+            uniq, inverse = torch.unique(t, return_inverse=True)
+            if uniq.numel() <= self.max_distinct_timesteps:
+                t, e_index = uniq.unsqueeze(0), inverse.to(torch.int32).contiguous()
         with torch.amp.autocast('cuda', dtype=torch.float32):
             bt, lt = t.shape
             e = self.time_embedding(sinusoidal_embedding_1d(self.freq_dim, t.flatten()).unflatten(0, (bt, lt)).float())
@@ -502,6 +521,8 @@ class WanModel(nn.Module):
             torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
         kwargs = dict(e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=context,
                       context_lens=None)
+        if e_index is not None:
+            kwargs['e_index'] = e_index
         return x, e, kwargs
 
     def forward(self, x, t, context, seq_len, y=None):
@@ -512,9 +533,15 @@ class WanModel(nn.Module):
         x, e, kwargs = self.embed(x, t, context, seq_len, y)
         for block in self.blocks:
             x = block(x, **kwargs)
-        x = self.head(x, e)
+        x = self.head(x, self.token_embedding(e, kwargs.get('e_index')))
         x = self.unpatchify(x, kwargs['grid_sizes'])
         return [u.float() for u in x]
+
+    @staticmethod
+    def token_embedding(e, e_index):
+        """The head's per-token time embedding [B, L, C] from the de-duplicated form (e [1, U, C], e_index [B, L]);
+        e is returned unchanged when there is no index."""
+        return e if e_index is None else e[0][e_index.long()]
 
     def unpatchify(self, x, grid_sizes):
         """[L, C_out * prod(patch)] token rows back to [C_out, F*pf, H*ph, W*pw] (model.py:499-522)."""

@@ -45,7 +45,7 @@ def cfg_batched_forward(model, latent, timestep, context, context_null, seq_len,
         kwargs['context'] = ctx * w
     for block in model.blocks:
         x = block(x, **kwargs)
-    x = model.head(x, e)
+    x = model.head(x, model.token_embedding(e, kwargs.get('e_index')))
     out = model.unpatchify(x, kwargs['grid_sizes'])
     return out[0].float(), out[1].float()
 
