@@ -38,6 +38,11 @@ CONFIGS = {
     # BASELINE.json configs[3]: Wan2.1-T2V-14B, 81 frames 720x1280 -> token grid (21, 45, 80)
     "14B": dict(name="Wan2.1-T2V-14B denoise step, 81f 720x1280", dim=5120, heads=40, layers=40, ffn=13824,
                 grid=(21, 45, 80), text_len=512),
+    # the reference's own default model (not a BASELINE config; SURVEY.md sec. 8 geometry table, "ref native"):
+    # Wan2.2 ti2v-5B (models/wan/configs/wan_ti2v_5B.py), 121 frames 704x1280 -> token grid (31, 22, 40), 48 latent
+    # channels, first latent frame given (its tokens carry timestep 0, textimage2video.py:372-377)
+    "5B": dict(name="Wan2.2-TI2V-5B denoise step, 121f 704x1280", dim=3072, heads=24, layers=30, ffn=14336,
+               grid=(31, 22, 40), text_len=512, in_dim=48, ti2v=True),
 }
 
 
@@ -391,18 +396,21 @@ def run_native_arm(args, cfg_key):
         torch.cuda.empty_cache()
         torch.manual_seed(0)
         with torch.device(dev):
-            model = mdl.WanModel(model_type="t2v", dim=dim, ffn_dim=cfg["ffn"], num_heads=heads, num_layers=layers,
-                                 text_len=text_len, in_dim=16, out_dim=16)
+            zc = cfg.get("in_dim", 16)
+            model = mdl.WanModel(model_type="ti2v" if cfg.get("ti2v") else "t2v", dim=dim, ffn_dim=cfg["ffn"],
+                                 num_heads=heads, num_layers=layers, text_len=text_len, in_dim=zc, out_dim=zc)
         model = model.eval()
         if world > 1:
             for block in model.blocks:
                 block.self_attn.forward = types.MethodType(sp.sp_attn_forward, block.self_attn)
             model.forward = types.MethodType(sp.sp_dit_forward, model)
         gen = torch.Generator(device=dev).manual_seed(7)      # identical inputs on every rank
-        lat = [torch.randn(16, f, h * 2, w * 2, device=dev, generator=gen)]
+        lat = [torch.randn(zc, f, h * 2, w * 2, device=dev, generator=gen)]
         ctx_in = [torch.randn(text_len, 4096, device=dev, generator=gen)]
         # per-token timesteps [1, seq_len], the way the reference sampling loop calls the DiT (textimage2video.py:372-377)
         tt = torch.full((1, L), 500.0, device=dev)
+        if cfg.get("ti2v"):
+            tt[0, :h * w] = 0.0
         with torch.no_grad(), torch.autocast("cuda", dtype=bf):
             model(lat, tt, ctx_in, seq_len=L)
             barrier()

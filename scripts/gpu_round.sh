@@ -9,6 +9,8 @@ echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_$TAG.err | tee gpurun_out/bench_$TAG.json
 tail -5 gpurun_out/bench_$TAG.err
 echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref_$TAG.json
+echo "== bench ti2v-5B (the reference's native model; not a BASELINE config)" ; timeout 600 python bench.py --config 5B --steps 3 --warmup 3 --skip-cpu 2>gpurun_out/bench_5B_$TAG.err | tee gpurun_out/bench_5B_$TAG.json | cut -c1-400
+tail -2 gpurun_out/bench_5B_$TAG.err
 echo "== bench tma-sweep" ; timeout 600 python bench.py --workload tma-sweep 2>gpurun_out/bench_sweep_$TAG.err | tee gpurun_out/bench_sweep_$TAG.json
 tail -3 gpurun_out/bench_sweep_$TAG.err
 echo "== kernel battery (prologue + cross)"
@@ -37,4 +39,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 echo "block launch list rows: $(wc -l < gpurun_out/launches_block_$TAG.csv)"
 echo "== denoise step by category (CUDA events)"
 python scripts/profile_denoise.py > gpurun_out/denoise_profile_$TAG.log 2>&1; cat gpurun_out/denoise_profile_$TAG.log
+echo "== sampler step / batched CFG / per-token timesteps"
+python scripts/bench_cfg_batch.py > gpurun_out/cfg_batch_$TAG.log 2>&1; tail -4 gpurun_out/cfg_batch_$TAG.log
+echo "== A/B inside the power-capped step: exp2 on the FMA pipe for 1 pair in 4 (UVB_FMHA_POLY=4) vs MUFU only"
+for v in 0 4 0 4; do
+  UVB_FMHA_POLY=$v timeout 300 python bench.py --steps 3 --warmup 3 --skip-cpu --skip-denoise 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('POLY=$v value', round(d['value'],1), 'fmha in-step', round(d['roofline']['achieved'],1), 'clk', d['clocks']['sm_mhz'])"
+done | tee gpurun_out/poly_ab_$TAG.log
 ls -la gpurun_out | tail -20

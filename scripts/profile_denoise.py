@@ -64,12 +64,15 @@ def main():
     mdl._ffn_forward = ffn
     torch.manual_seed(0)
     with torch.device(dev):
+        zc = cfg.get("in_dim", 16)
         model = mdl.WanModel(model_type="t2v", dim=cfg["dim"], ffn_dim=cfg["ffn"], num_heads=cfg["heads"],
-                             num_layers=cfg["layers"], text_len=cfg["text_len"], in_dim=16, out_dim=16).eval()
+                             num_layers=cfg["layers"], text_len=cfg["text_len"], in_dim=zc, out_dim=zc).eval()
     gen = torch.Generator(device=dev).manual_seed(7)
-    lat = [torch.randn(16, f, h * 2, w * 2, device=dev, generator=gen)]
+    lat = [torch.randn(zc, f, h * 2, w * 2, device=dev, generator=gen)]
     ctx = [torch.randn(cfg["text_len"], 4096, device=dev, generator=gen)]
-    tt = torch.tensor([500.0], device=dev)
+    tt = torch.full((1, L), 500.0, device=dev)           # per-token timesteps, like the reference loop
+    if cfg.get("ti2v"):
+        tt[0, :h * w] = 0.0
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         model(lat, tt, ctx, seq_len=L)
         torch.cuda.synchronize()
