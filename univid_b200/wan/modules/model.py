@@ -139,13 +139,20 @@ _USE_GEMM = os.environ.get('UVB_LINEAR', '1') != '0'
 _LINEAR_CACHE = {}
 
 
+def _version_of(t):
+    try:
+        return t._version
+    except RuntimeError:           # inference tensors do not track a version: never cache-hit on them
+        return object()
+
+
 def _linear_operands(mod):
     """(weight bf16 [N, K], bias fp32 [N] holding bf16-rounded values | None) of an nn.Linear, cached until the
     parameters change: autocast casts weight AND bias to bf16 on every call (the reference pays that cast per
     autocast region); here the copy is made once per parameter version."""
     w, b = mod.weight, mod.bias
     key = id(w)
-    ver = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+    ver = (_version_of(w), w.data_ptr(), None if b is None else (_version_of(b), b.data_ptr()))
     hit = _LINEAR_CACHE.get(key)
     if hit is not None and hit[0]() is w and hit[1] == ver:
         return hit[2], hit[3]
