@@ -25,7 +25,7 @@ def libpath():
 def test_header_declares_the_hot_path_entry_points():
     syms = _declared_symbols()
     for name in ("uvb_qk_norm_rope", "uvb_fmha_fwd_bf16", "uvb_xattn_fwd_bf16", "uvb_head_scatter_bf16",
-                 "uvb_last_error", "uvb_version"):
+                 "uvb_last_error", "uvb_version", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step"):
         assert name in syms
 
 
@@ -45,7 +45,8 @@ def test_python_binding_lists_the_same_symbols(libpath):
 def test_header_cites_reference_call_sites():
     src = open(HEADER).read()
     for cite in ("attention.py:96,113,175", "model.py:77-85", "model.py:38-66", "util.py:27",
-                 "model_pipeline.py:1756-1803"):
+                 "model_pipeline.py:1756-1803", "model.py:119-122", "model.py:212-214", "fm_solvers_unipc.py:657-741",
+                 "textimage2video.py:385-386"):
         assert cite in src
 
 
@@ -60,6 +61,9 @@ def test_library_contains_blackwell_instructions(libpath):
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass and "HGMMA" not in sass
+    # the GEMM's CTA-pair variant: cta_group::2 MMA, pair TMA loads, multicast commit
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_missing_library_fails_loudly(monkeypatch):
