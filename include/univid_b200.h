@@ -155,11 +155,15 @@ int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* cons
  *   mod_index: DEVICE int32 [B*L] or NULL.  When given, token (b, l) reads modulation row mod_index[b*L + l] instead
  *   of row l: the reference expands the timestep to one value per token (textimage2video.py:372-377, model.py:460-468)
  *   and materialises [B, L, 6, dim]; with few distinct timesteps one row per distinct value is enough.
+ *   ln_round_bf16 != 0: the LayerNorm result (after the affine) is rounded to bf16 before the modulation.  This is
+ *   WanLayerNorm's `.type_as(x)` (model.py:98) for a bf16 x -- the first block of the DiT receives the bf16 output of
+ *   the patch embedding (model.py:447, under autocast); the caller passes that x widened to fp32 (exact).
  *   dim in {256, 512, 1024, 1536, 2048, 3072, 4096, 5120}; all pointers 16-byte aligned.
  */
 int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x_out, const float* ln_w,
                    const float* ln_b, const float* scale, const float* shift, void* h_out, int B, int L,
-                   int dim, int64_t mod_sb, int64_t mod_sl, const int32_t* mod_index, float eps, void* stream);
+                   int dim, int64_t mod_sb, int64_t mod_sl, const int32_t* mod_index, float eps, int ln_round_bf16,
+                   void* stream);
 
 /* Diagnostics: when set to a DEVICE buffer of (number of SMs) x 32 uint64, every attention launch records
  * per CTA {smid, start ns, end ns of each piece of work (up to 30)} (%globaltimer).  NULL (default) = off. */

@@ -103,6 +103,39 @@ def test_model_forward_with_per_token_timesteps_deduplicated():
     assert (got - uni).abs().max() > 1e-3                                  # the per-token values really matter
 
 
+def test_first_block_with_bf16_input_takes_the_fused_path():
+    """The first block of the DiT receives the bf16 output of the patch embedding (model.py:447 under autocast):
+    WanLayerNorm then returns bf16 (.type_as, model.py:98).  The fused glue reproduces that rounding point
+    (ln_round_bf16); checked against the eager expression of the same module and against the oracle."""
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    from univid_b200 import _ext
+    case = block_case(3, False)
+    freqs = orc.make_freqs(128)
+    xb = case["x"].to(torch.bfloat16)
+    want32 = orc.attention_block(xb, case["e"], case["prm"], case["seq_lens"], case["grid_sizes"], freqs,
+                                 case["context"], None, HEADS, eps=EPS, bf16=False)
+    blk = mdl.WanAttentionBlock(DIM, FFN, HEADS, cross_attn_norm=True, eps=EPS)
+    blk.load_state_dict(case["prm"])
+    blk = blk.cuda().eval()
+    args = (xb.cuda(), case["e"].cuda(), case["seq_lens"], case["grid_sizes"], freqs.cuda(), case["context"].cuda(), None)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert blk._fused_glue_ok(args[0], args[1])
+        got = blk(*args)
+        blk._fused_glue_ok = lambda *a: False
+        eager = blk(*args)
+    assert got.dtype == torch.float32 and eager.dtype == torch.float32
+    assert (got - eager).abs().max().item() <= 2e-2
+    assert (got.cpu() - want32).abs().max().item() <= 2e-2 and _cos(got.cpu(), want32) >= 0.9999
+    # the kernel-level rounding point: LN rounded to bf16, then modulated
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 19, 1536, generator=g).to(torch.bfloat16).float().cuda()
+    mod = (0.3 * torch.randn(2, 1, 2, 1536, generator=g)).cuda()
+    _, h = _ext.block_glue(x, scale=mod[:, :, 1], shift=mod[:, :, 0], eps=1e-6, ln_round_bf16=True)
+    ln = torch.nn.functional.layer_norm(x, (1536,), None, None, 1e-6).to(torch.bfloat16).float()
+    want = torch.addcmul(mod[:, :, 0], ln, 1 + mod[:, :, 1]).to(torch.bfloat16)
+    assert (h == want).float().mean() > 0.99 and (h.float() - want.float()).abs().max() <= 0.0079 * want.float().abs().max()
+
+
 @pytest.mark.parametrize("per_tok", [False, True])
 def test_block_matches_oracle(per_tok):
     """Fused block vs the oracle (bit-exactly pinned to the reference block by tests/test_block_oracle_golden.py):

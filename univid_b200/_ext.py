@@ -18,7 +18,7 @@ EXPORTS = (
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step",
 )
-ABI_VERSION = 106
+ABI_VERSION = 107
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -85,7 +85,7 @@ def lib():
     L.uvb_sp_wait.restype = _i
     L.uvb_sp_wait.argtypes = [_vp, _i, _u32, _vp]
     L.uvb_block_glue.restype = _i
-    L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _vp, _f, _vp]
+    L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _vp, _f, _i, _vp]
     L.uvb_linear_bf16.restype = _i
     L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
     L.uvb_unipc_step.restype = _i
@@ -369,12 +369,13 @@ GLUE_DIMS = (256, 512, 1024, 1536, 2048, 3072, 4096, 5120)
 
 
 def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, want_h=True, inplace=False,
-               index=None):
+               index=None, ln_round_bf16=False):
     """Fused residual / LayerNorm / adaLN glue of a WanAttentionBlock (uvb_block_glue):
         x' = x + y * gate   (if y is given; a new tensor unless inplace)   h = LN(x')[* w + b] * (1 + scale) + shift -> bf16
     x fp32 [B, L, dim] contiguous; y bf16 [B, L, dim]; gate / scale / shift fp32 [B, 1 or L, dim] views with
     unit stride over dim (chunks of the modulation tensor); ln = None | (weight, bias).
     index: int32 [B, L] or None -- token (b, l) uses modulation row index[b, l]; the chunks are then [1 or B, U, dim].
+    ln_round_bf16: round the LayerNorm result to bf16 before the modulation (WanLayerNorm's .type_as(x) for a bf16 x).
     Returns (x', h)."""
     global launch_count
     _require_cuda(x, y, gate, scale, shift, index)
@@ -417,7 +418,8 @@ def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, 
     x_new = x if (y is None or inplace) else torch.empty_like(x)
     _check(lib().uvb_block_glue(_ptr(x), _ptr(y), _ptr(gate), _ptr(x_new) if y is not None else None, _ptr(lw),
                                 _ptr(lb), _ptr(scale), _ptr(shift), _ptr(h), B, L, dim, sb or 0, sl or 0,
-                                _ptr(index) if sb is not None else None, float(eps), _stream(x)))
+                                _ptr(index) if sb is not None else None, float(eps), 1 if ln_round_bf16 else 0,
+                                _stream(x)))
     launch_count += 1
     return x_new, h
 

@@ -38,6 +38,9 @@ struct BlockGlueParams {
   const int* mod_index;         // [rows] or nullptr: modulation row of each token (instead of its position l) --
                                 // per-token timesteps with few distinct values keep one row per value
   float eps;
+  int ln_round_bf16;            // 1: round the LayerNorm result to bf16 before the modulation -- WanLayerNorm returns
+                                // its input's dtype (model.py:98), which is bf16 for the first block of the DiT (the
+                                // patch embedding runs under autocast); the caller widens that x to fp32 (exact)
 };
 
 constexpr int kGlueWarps = 8;
@@ -164,6 +167,10 @@ __global__ void __launch_bounds__(kGlueWarps * 32) block_glue_kernel(const __gri
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) h[e] += bb[e];
+    }
+    if (p.ln_round_bf16) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = __bfloat162float(__float2bfloat16_rn(h[e]));
     }
     if (p.scale != nullptr) {
       const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + mod_off + c));

@@ -393,7 +393,7 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 106; }
+int uvb_version(void) { return 107; }
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -533,7 +533,8 @@ int uvb_fmha_fwd_bf16(const void* q, const void* k, const void* v, void* o, cons
 
 int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x_out, const float* ln_w,
                    const float* ln_b, const float* scale, const float* shift, void* h_out, int B, int L,
-                   int dim, int64_t mod_sb, int64_t mod_sl, const int32_t* mod_index, float eps, void* stream) {
+                   int dim, int64_t mod_sb, int64_t mod_sl, const int32_t* mod_index, float eps, int ln_round_bf16,
+                   void* stream) {
   if (x_in == nullptr) return fail(UVB_ERR_INVALID, "x_in is null");
   if (B <= 0 || L <= 0 || dim <= 0) return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d dim=%d", B, L, dim);
   if (y == nullptr && h_out == nullptr) return fail(UVB_ERR_INVALID, "nothing to do (y and h_out are both null)");
@@ -567,6 +568,7 @@ int uvb_block_glue(const float* x_in, const void* y, const float* gate, float* x
   p.mod_sl = mod_sl;
   p.mod_index = mod_index;
   p.eps = eps;
+  p.ln_round_bf16 = ln_round_bf16 != 0 ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 block(uvb::kGlueWarps * 32);
   auto blocks = [&](int wpr) {

@@ -372,8 +372,9 @@ class WanAttentionBlock(nn.Module):
 
     def _fused_glue_ok(self, x, mod):
         """The fused glue kernel covers the inference configuration of the product: fp32 residual stream on the
-        GPU, bf16 autocast (so the branch outputs are bf16), no autograd, plain WanLayerNorm / Identity norms."""
-        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.size(-1) in _ext.GLUE_DIMS
+        GPU (or the bf16 output of the patch embedding entering the first block), bf16 autocast (so the branch
+        outputs are bf16), no autograd, plain WanLayerNorm / Identity norms."""
+        return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 3 and x.size(-1) in _ext.GLUE_DIMS
                 and torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
                 and not (torch.is_grad_enabled() and (x.requires_grad or mod.requires_grad))
                 and type(self.norm1) is WanLayerNorm and type(self.norm2) is WanLayerNorm
@@ -384,9 +385,12 @@ class WanAttentionBlock(nn.Module):
         """Same dataflow as above with the elementwise glue in uvb_block_glue: one pass per residual update,
         producing the next branch's bf16 input in the same pass."""
         shift_a, scale_a, gate_a, shift_f, scale_f, gate_f = mods
-        x = x.contiguous()
+        # a bf16 x (first block: the patch embedding ran under autocast) is widened to fp32 -- exact -- and norm1's
+        # result is rounded to bf16 like WanLayerNorm's .type_as(x) does; the residual `x + y * gate` is fp32 either way
+        first_bf16 = x.dtype == torch.bfloat16
+        x = x.float().contiguous()
         ix = e_index
-        _, h = _ext.block_glue(x, scale=scale_a, shift=shift_a, eps=self.norm1.eps, index=ix)
+        _, h = _ext.block_glue(x, scale=scale_a, shift=shift_a, eps=self.norm1.eps, index=ix, ln_round_bf16=first_bf16)
         y = self.self_attn(h, seq_lens, grid_sizes, freqs)
         if isinstance(self.norm3, WanLayerNorm):
             ln3 = (self.norm3.weight, self.norm3.bias) if self.norm3.elementwise_affine else (None, None)
