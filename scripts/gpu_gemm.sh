@@ -24,4 +24,11 @@ for c in 1 2; do
   run gemm 75600 5120 13824 0 3
   run gemm 75600 13824 5120 1 3
 done
+ENVV=""
+run gemm 512 1536 1536 0 20
+run gemm 512 5120 5120 0 20
+run gemm 1 1536 1536 1 0
+run gemm 130 200 72 1 0
+ENVV="UVB_GEMM_SMALL=0"
+run gemm 512 1536 1536 0 20
 cat $LOG

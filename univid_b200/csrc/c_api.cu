@@ -697,6 +697,14 @@ int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, in
   }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int workers = 0;
+  // Small problems (the 512 context rows of the cross-attention k / v projections, single-row probes): when 128 x 64
+  // tiles of single CTAs fit in ONE wave, latency is what counts -- many small tiles instead of a dozen 256-wide pairs.
+  static const bool allow_small = [] {
+    const char* e = getenv("UVB_GEMM_SMALL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const long long small_tiles = static_cast<long long>((M + uvb::kGemmBM - 1) / uvb::kGemmBM) * ((N + 63) / 64);
+  if (allow_small && small_tiles <= sms) return launch_gemm<1, 64>(p, x, w, y, ldx, ldw, ldy, sms, st);
   if (ctas == 2) {
     if ((rc = gemm_workers<2>(sms, &workers)) != UVB_OK) return rc;
     return pick_tile_n<2>(p, workers) == 192 ? launch_gemm<2, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)

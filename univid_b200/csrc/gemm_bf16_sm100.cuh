@@ -13,6 +13,7 @@
 // (N = 1536 on 74 pairs: 10.4 waves of 256-wide tiles, 13.8 of 192-wide ones).  TMEM holds two 128 x kBN fp32
 // accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  Shared memory: kStages x (A 16 KiB +
 // B kBN/kCtas x 128 B) ring, two 16 KiB output staging panels.
+// Problems whose 128 x 64 tiles fit in one wave of single CTAs (a few hundred rows) run as <1, 64>: latency-bound.
 // Tiles are dealt round-robin to the persistent CTAs in an order that walks `group_n` column tiles for each row
 // tile before moving down; the host sizes the group so that its slab of B (group_n x kBN x K) stays in L2 while
 // A streams past once per group.  Ragged M / N / K edges are handled by TMA (zero fill on load, clipping on store).
