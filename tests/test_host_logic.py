@@ -249,3 +249,30 @@ def test_embed_deduplicates_per_token_timesteps():
     with torch.no_grad():
         _, _, kw2 = model.embed(lat, t, ctx, L)
     assert "e_index" not in kw2 and kw2["e"].shape == (2, L, 6, 256)
+
+
+def test_every_kernel_wrapper_refuses_cpu_tensors():
+    """No CPU fallback anywhere on the product path: each tensor-level wrapper of the C ABI raises on CPU tensors
+    instead of computing something else (the drop-in modules then fail loudly on a machine without the GPU)."""
+    import torch
+    from univid_b200 import _ext
+    bf = torch.bfloat16
+    x = torch.zeros(1, 4, 256)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.linear(x.to(bf), torch.zeros(256, 256, dtype=bf))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.block_glue(x, scale=torch.zeros(1, 1, 256), shift=torch.zeros(1, 1, 256))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.head_scatter(torch.zeros(1, 4, 2, 128, dtype=bf), 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.unipc_step(torch.zeros(8), None, torch.zeros(8), None, None, None, _ext.UnipcCoef())
+    q = torch.zeros(1, 4, 2, 128, dtype=bf)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.fmha_fwd(q, q, q)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _ext.qk_norm_rope(x.to(bf), None, torch.ones(256), None, 1e-6, 2)
+    # the modules built on them: a CPU call of the attention classes cannot silently run another implementation
+    mdl = importlib.import_module("univid_b200.wan.modules.model")
+    sa = mdl.WanSelfAttention(256, 2)
+    with pytest.raises((RuntimeError, AssertionError)):
+        sa(x, torch.tensor([4]), torch.tensor([[1, 2, 2]]), mdl.rope_params(1024, 128)[:, :64])
