@@ -317,7 +317,9 @@ def run_native_arm(args, cfg_key):
                              "achieved": pbytes / (pavg * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"],
                              "peak_source": peaks["source"] + " copy bandwidth", "avg_launch_ms": pavg,
-                             "bytes_per_launch": pbytes, "traffic": None}
+                             "bytes_per_launch": pbytes,
+                             "traffic": (json.load(open(tpath)).get(cfg_key, {}).get("prologue_dram_bytes_per_launch")
+                                         if os.path.exists(tpath) else None)}
 
     # ---------------- the block's largest GEMM (ffn[0] + tanh-GELU), timed live -----
     roofline_gemm = None
