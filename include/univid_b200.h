@@ -37,6 +37,23 @@ int uvb_version(void);
 /* Message of the last failing call on this thread ("" if none). */
 const char* uvb_last_error(void);
 
+/* Explicit, process-wide tuning knobs.  The library never reads environment variables: kernel selection
+ * changes only through this call (benchmarks and A/B scripts use it; a product never has to).  The
+ * defaults are the shipped configuration.  uvb_set_knob returns 0 or UVB_ERR_INVALID; uvb_get_knob
+ * returns the value (>= 0) or UVB_ERR_INVALID.  (No reference counterpart: the reference selects its
+ * attention backend with module-level flags, attention.py:4-17.) */
+enum uvb_knob {
+  UVB_KNOB_FMHA_PAIR = 0,     /* 1: CTA-pair (cta_group::2) attention kernel for Lk > 2048 (default); 0: single CTAs */
+  UVB_KNOB_FMHA_SPLIT = 1,    /* 1: stream-K split of the remainder query blocks (default); 0: never split */
+  UVB_KNOB_GEMM_CTAS = 2,     /* 2: CTA-pair GEMM tiles (default); 1: single-CTA tiles */
+  UVB_KNOB_GEMM_BN = 3,       /* 0: tile width chosen per problem (default); 192 | 256: pinned */
+  UVB_KNOB_GEMM_SMALL = 4,    /* 1: one-wave 128x64 tiles for small problems (default); 0: off */
+  UVB_KNOB_PROLOGUE_PAIR = 5, /* 1: token-pair q/k prologue kernel (default); 0: one row per warp group */
+  UVB_KNOB_COUNT = 6
+};
+int uvb_set_knob(int knob, int value);
+int uvb_get_knob(int knob);
+
 /* Fused WanRMSNorm(q), WanRMSNorm(k) over the full width dim = N*128, followed by the 3-D RoPE.
  * Replaces: WanRMSNorm.forward (model.py:77-85) x2 + rope_apply (model.py:38-66) x2 of
  * WanSelfAttention.forward (model.py:137-147); with cos_sin == NULL it is the norm-only prologue of

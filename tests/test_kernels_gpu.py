@@ -118,11 +118,42 @@ def test_fmha_matches_oracle(ext, b, lq, lk, n):
     _check_attn(got, orc.attention_varlen(q, k, v, compute_dtype=torch.float32))
 
 
+@pytest.mark.parametrize("b,lq,lk,n,lens", [(1, 2100, 2100, 1, None), (1, 4000, 2500, 2, None), (2, 513, 2200, 3, [2200, 100]),
+                                             (1, 512, 2304, 1, None), (1, 130, 3000, 2, None), (1, 1025, 2049, 2, [2049]),
+                                             (2, 700, 4500, 2, [0, 4500])])
+def test_fmha_cta_pair_kernel(ext, b, lq, lk, n, lens):
+    """Lk > 2048 runs the CTA-pair kernel (cta_group::2: 512-row units over two CTAs, K / V halves per CTA, remote
+    p_full arrives): against the oracle, and against the single-CTA kernel selected through uvb_set_knob.  Shapes
+    cover a ragged last unit (rows of only the leader CTA / only its first tile valid), ragged key tiles whose
+    second 64-key half is entirely out of bounds, k_lens (incl. 0) and more units than CTA pairs."""
+    g = torch.Generator().manual_seed(lq * 3 + lk)
+    q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+    kl = None if lens is None else torch.tensor(lens, dtype=torch.int32)
+    klc = None if kl is None else kl.cuda()
+    assert ext.lib().uvb_get_knob(ext.KNOBS["fmha_pair"]) == 1
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=klc)
+    got_nosplit = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=klc, split_units=False)
+    old = ext.set_knob("fmha_pair", 0)
+    try:
+        single = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=klc)
+    finally:
+        ext.set_knob("fmha_pair", old)
+    want = orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32)
+    _check_attn(got, want)
+    _check_attn(got_nosplit, want)
+    assert (got.float() - single.float()).abs().max().item() <= 4e-3
+
+
 def test_fmha_peaked_logits_exercise_the_lazy_rescale(ext):
     """Row maxima that grow by far more than 2^8 from one key tile to the next force the in-place
     rescale of the TMEM accumulator."""
     g = torch.Generator().manual_seed(1)
     lq, lk = 256, 1024
+    _peaked(ext, g, lq, lk)
+    _peaked(ext, g, 600, 2560)          # CTA-pair kernel
+
+
+def _peaked(ext, g, lq, lk):
     q = torch.randn(1, lq, 2, 128, generator=g)
     k = torch.randn(1, lk, 2, 128, generator=g)
     k = k * torch.linspace(0.2, 6.0, lk).view(1, lk, 1, 1)      # logits grow along the key axis
@@ -184,7 +215,9 @@ def test_unsupported_shapes_raise(ext):
         ext.fmha_fwd(q, q, q)
 
 
-@pytest.mark.parametrize("p,s,heads,batch", [(2, 120, 4, 1), (4, 60, 4, 1), (2, 256, 2, 2), (8, 45, 8, 1), (2, 130, 6, 1)])
+@pytest.mark.parametrize("p,s,heads,batch", [(2, 120, 4, 1), (4, 60, 4, 1), (2, 256, 2, 2), (8, 45, 8, 1), (2, 130, 6, 1),
+                                             # > 2048 keys: the CTA-pair attention kernel does the peer stores
+                                             (2, 1100, 2, 1), (4, 640, 4, 1), (8, 300, 8, 2)])
 def test_sp_kernels_with_local_peers(ext, p, s, heads, batch):
     """The fused Ulysses exchange kernels (uvb_*_sp) on ONE GPU: the p 'peer' buffers are p local buffers, and the
     p ranks run one after the other.  Checks the peer-store addressing of the prologue / head scatter, the

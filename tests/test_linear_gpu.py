@@ -56,15 +56,16 @@ def test_linear_matches_fp32(M, N, K, bias, act):
 
 @pytest.mark.parametrize("ctas", ["1", "2"])
 def test_both_kernel_variants_in_the_standalone_binary(ctas):
-    """The library reads UVB_GEMM_CTAS once per process (1 = one CTA per tile, default = CTA pairs): run the C
-    battery case of the stand-alone binary under each setting (it checks against a naive fp32-accumulate kernel)."""
+    """uvb_set_knob(UVB_KNOB_GEMM_CTAS, 1 | 2) selects one CTA per tile or CTA pairs (default): run the C battery case
+    of the stand-alone binary under each setting (the test binary maps UVB_KNOBS onto uvb_set_knob; it checks
+    against a naive fp32-accumulate kernel)."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "univid_b200", "csrc", "tests", "uvb_test")
     assert os.path.exists(exe), "build the test binary with `python -m univid_b200.build`"
     for case in (["gemm", "1000", "1536", "1536", "1", "0"], ["gemm", "520", "2296", "200", "0", "0"]):
-        r = subprocess.run([exe] + case, env=dict(os.environ, UVB_GEMM_CTAS=ctas), capture_output=True, text=True,
+        r = subprocess.run([exe] + case, env=dict(os.environ, UVB_KNOBS=f"gemm_ctas={ctas}"), capture_output=True, text=True,
                            timeout=120)
         assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 

@@ -16,9 +16,10 @@ EXPORTS = (
     "uvb_fmha_fwd_bf16", "uvb_fmha_workspace_bytes", "uvb_xattn_fwd_bf16", "uvb_debug_fmha_timeline",
     "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
-    "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step",
+    "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step", "uvb_set_knob", "uvb_get_knob",
 )
-ABI_VERSION = 107
+ABI_VERSION = 108
+KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5}
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -90,11 +91,22 @@ def lib():
     L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
     L.uvb_unipc_step.restype = _i
     L.uvb_unipc_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _c.POINTER(UnipcCoef), _vp]
+    L.uvb_set_knob.restype = _i
+    L.uvb_set_knob.argtypes = [_i, _i]
+    L.uvb_get_knob.restype = _i
+    L.uvb_get_knob.argtypes = [_i]
     if L.uvb_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB_PATH} has ABI version {L.uvb_version()}, expected {ABI_VERSION}: rebuild it "
                            "with `python -m univid_b200.build --force`")
     _lib = L
     return L
+
+
+def set_knob(name, value):
+    """Explicit tuning knob of the library (uvb_set_knob; names in KNOBS).  Returns the previous value."""
+    old = lib().uvb_get_knob(KNOBS[name])
+    _check(lib().uvb_set_knob(KNOBS[name], int(value)))
+    return old
 
 
 def _check(rc):

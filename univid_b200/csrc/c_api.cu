@@ -52,6 +52,17 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// Explicit tuning knobs (uvb_set_knob): process-wide, changed only by an API call -- the library never reads
+// the environment.  Defaults are the shipped configuration.
+int g_knobs[UVB_KNOB_COUNT] = {
+    /* UVB_KNOB_FMHA_PAIR     */ 1,   // CTA-pair attention kernel for long key sequences
+    /* UVB_KNOB_FMHA_SPLIT    */ 1,   // stream-K split of the remainder units
+    /* UVB_KNOB_GEMM_CTAS     */ 2,   // 2 = CTA pairs (cta_group::2), 1 = single CTAs
+    /* UVB_KNOB_GEMM_BN       */ 0,   // 0 = per-problem choice, 192 | 256 pins the tile width
+    /* UVB_KNOB_GEMM_SMALL    */ 1,   // single-wave 128x64 tiles for small problems
+    /* UVB_KNOB_PROLOGUE_PAIR */ 1,   // token-pair prologue kernel when q and k are both given
+};
+
 int check_device() {
   static int ok_dev = -1;
   int dev = 0;
@@ -67,7 +78,8 @@ int check_device() {
 }
 
 // [B, L, N, 128] bf16 viewed as (d, token, head, batch); box = one 64-column panel of a 128-token tile
-int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const int64_t* strides) {
+int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const int64_t* strides,
+                  int box_rows = 128) {
   EncodeTiledFn enc = get_encode_tiled();
   if (enc == nullptr) return fail(UVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   int64_t sb = static_cast<int64_t>(L) * N * 128, sl = static_cast<int64_t>(N) * 128, sh = 128;
@@ -84,7 +96,7 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int L, int N, const 
                               static_cast<cuuint64_t>(B)};
   const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(sl) * 2, static_cast<cuuint64_t>(sh) * 2,
                               static_cast<cuuint64_t>(sb) * 2};
-  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -203,10 +215,7 @@ int gemm_workers(int sms, int* out) {
 // (less operand reuse) but often fill the last wave better (N = 1536: 10.4 -> 13.8 waves).
 template <int kCtas>
 int pick_tile_n(const uvb::GemmParams& p, int workers) {
-  static const int forced = [] {
-    const char* e = getenv("UVB_GEMM_BN");
-    return e != nullptr ? atoi(e) : 0;
-  }();
+  const int forced = g_knobs[UVB_KNOB_GEMM_BN];
   if (forced == 192 || forced == 256) return forced;
   const long long n_m = (p.M + uvb::kGemmBM * kCtas - 1) / (uvb::kGemmBM * kCtas);
   auto cost = [&](int bn, double penalty) {
@@ -238,6 +247,40 @@ size_t fmha_ws_bytes(int sms) {
   return kWsFlagBytes + static_cast<size_t>(sms) * uvb::kWsSlotFloats * sizeof(float);
 }
 
+constexpr int kPairStages = 8;       // K/V ring slots of 16 KiB in the CTA-pair attention kernel
+
+// CTA pairs of the attention kernel the device can hold at once (one per TPC); also sets the kernel's
+// shared-memory attribute for the current device.  0 pairs = fall back to single CTAs.
+int fmha_pair_workers(int sms, int* out) {
+  static int cached_dev = -1, cached = 0;
+  int dev = 0;
+  UVB_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    using SM = uvb::FmhaSmem<kPairStages, 1, 2>;
+    auto kern = uvb::fmha_fwd_kernel<kPairStages, 1, 2, false>;
+    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(uvb::kFmhaThreads);
+    cfg.dynamicSmemBytes = SM::kDynBytes;
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    UVB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    cached = n < sms / 2 ? n : sms / 2;
+    if (cached < 0) cached = 0;
+    cached_dev = dev;
+  }
+  *out = cached;
+  return UVB_OK;
+}
+
 template <bool kKeyMod>
 int launch_fmha(const void* q, const void* k, const void* v, void* o, const int32_t* k_lens,
                 const float* key_logit_scale, const float* key_pv_weight, const float* out_bias,
@@ -262,6 +305,7 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   memset(&p, 0, sizeof(p));
   if ((rc = make_tile_map(&p.tm_q, q, B, Lq, N, qs)) != UVB_OK) return rc;
   if ((rc = make_tile_map(&p.tm_k, k, B, Lk, N, ks)) != UVB_OK) return rc;
+  if ((rc = make_tile_map(&p.tm_kh, k, B, Lk, N, ks, 64)) != UVB_OK) return rc;
   if ((rc = make_tile_map(&p.tm_v, v, B, Lk, N, vs)) != UVB_OK) return rc;
   if (n_peers == 0) {
     if ((rc = make_tile_map(&p.tm_o, o, B, Lq, N, os)) != UVB_OK) return rc;
@@ -285,25 +329,32 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.Lq = Lq;
   p.Lk = Lk;
   p.N = N;
-  p.n_qt = (Lq + uvb::kUnitRows - 1) / uvb::kUnitRows;
+  const long long n_kv = (Lk + uvb::kBlockN - 1) / uvb::kBlockN;
+  // Few key tiles per query block (cross-attention: 4): the per-block prologue/epilogue dominates, so use
+  // the variant that prefetches the next block's Q and drains O through a second buffer (3 ring slots);
+  // long key sequences keep the deeper K/V ring instead -- and, for plain attention, run as CTA pairs
+  // (cta_group::2: 512-row units, half of every K / V tile per CTA).
+  const bool short_keys = n_kv <= kShortKeyTiles;
+  int pairs = 0;
+  if (!short_keys && !kKeyMod && g_knobs[UVB_KNOB_FMHA_PAIR] != 0) {
+    if ((rc = fmha_pair_workers(sms, &pairs)) != UVB_OK) return rc;
+  }
+  const bool pair = pairs > 0;
+  const int unit_rows = uvb::kUnitRows * (pair ? 2 : 1);
+  const int workers = pair ? pairs : sms;            // CTAs (or CTA pairs) walking the unit list
+  p.n_qt = (Lq + unit_rows - 1) / unit_rows;
   const long long units = static_cast<long long>(B) * N * p.n_qt;
   if (units > 0x7fffffffLL) return fail(UVB_ERR_INVALID, "too many query blocks");
   p.n_units = static_cast<int>(units);
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timeline = g_timeline;
 
-  // Tuning hook (read once): UVB_FMHA_SPLIT=0 disables the split of the remainder units across CTAs.
-  static const bool allow_split = [] {
-    const char* e = getenv("UVB_FMHA_SPLIT");
-    return e == nullptr || atoi(e) != 0;
-  }();
   // Persistent grid: one CTA per SM; with a workspace the remainder units are cut into equal key ranges
   // (then even fewer units than SMs keep every SM busy).
-  const long long n_kv = (Lk + uvb::kBlockN - 1) / uvb::kBlockN;
-  long long grid_x = units < sms ? units : sms;
+  long long grid_w = units < workers ? units : workers;
   // Splitting pays when a query block spans many key tiles; with a handful (cross-attention: 4) a partial
   // costs almost as much as a whole block (Q load, 128 KiB partial through L2, merge), so those never split.
-  if (workspace != nullptr && allow_split && n_kv > kShortKeyTiles) {
+  if (workspace != nullptr && g_knobs[UVB_KNOB_FMHA_SPLIT] != 0 && !short_keys) {
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
       return fail(UVB_ERR_INVALID, "workspace must be 256-byte aligned");
     if (workspace_bytes < static_cast<int64_t>(fmha_ws_bytes(sms)))
@@ -312,26 +363,33 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     p.flags = static_cast<uint32_t*>(workspace);
     p.ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsFlagBytes);
     const long long iters = units * n_kv;
-    grid_x = iters < sms ? iters : sms;
+    grid_w = iters < workers ? iters : workers;
   }
 
-  // Few key tiles per query block (cross-attention: 4): the per-block prologue/epilogue dominates, so use
-  // the variant that prefetches the next block's Q and drains O through a second buffer (3 ring slots);
-  // long key sequences keep the deeper K/V ring instead.
-  const bool short_keys = n_kv <= kShortKeyTiles;
-  // UVB_FMHA_POLY=N (experiment hook): one exp2 pair in every N goes through the FMA-pipe polynomial
-  static const int poly = [] {
-    const char* e = getenv("UVB_FMHA_POLY");
-    return e != nullptr ? atoi(e) : 0;
-  }();
-  void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 0, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 0, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 4) kern = uvb::fmha_fwd_kernel<3, 1, 4, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 8) kern = uvb::fmha_fwd_kernel<3, 1, 8, kKeyMod>;
-  if (!short_keys && !kKeyMod && poly == 3) kern = uvb::fmha_fwd_kernel<3, 1, 3, kKeyMod>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(uvb::kFmhaThreads);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  if (pair) {
+    auto kern = uvb::fmha_fwd_kernel<kPairStages, 1, 2, false>;
+    cfg.dynamicSmemBytes = uvb::FmhaSmem<kPairStages, 1, 2>::kDynBytes;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * grid_w));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));      // (max dynamic smem was set by fmha_pair_workers)
+    return UVB_OK;
+  }
+  void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 1, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 1, kKeyMod>;
   const int smem = short_keys ? uvb::FmhaSmem<3, 2>::kDynBytes : uvb::FmhaSmem<4, 1>::kDynBytes;
   UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<dim3(static_cast<unsigned>(grid_x)), uvb::kFmhaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  UVB_CUDA(cudaGetLastError());
+  cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(static_cast<unsigned>(grid_w));
+  UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return UVB_OK;
 }
 
@@ -339,13 +397,9 @@ template <typename InT, bool kPeers>
 int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
   const int dim = p.N * 128;
   const dim3 block(uvb::kNormRopeWarps * 32);
-  // q and k together (self-attention): one warp group per token, both rows in flight; UVB_PROLOGUE_PAIR=0
-  // keeps the one-row-per-group kernel (A/B hook)
-  static const bool allow_pair = [] {
-    const char* e = getenv("UVB_PROLOGUE_PAIR");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  const bool pair = allow_pair && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
+  // q and k together (self-attention): one warp group per token, both rows in flight (UVB_KNOB_PROLOGUE_PAIR = 0
+  // keeps the one-row-per-group kernel)
+  const bool pair = g_knobs[UVB_KNOB_PROLOGUE_PAIR] != 0 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
                     p.row_scale == nullptr && sizeof(InT) == 2;
   if (pair) {
     const long long tokens = static_cast<long long>(p.B) * p.L;
@@ -393,7 +447,18 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int uvb_version(void) { return 107; }
+int uvb_version(void) { return 108; }
+
+int uvb_set_knob(int knob, int value) {
+  if (knob < 0 || knob >= UVB_KNOB_COUNT) return fail(UVB_ERR_INVALID, "unknown knob %d", knob);
+  g_knobs[knob] = value;
+  return UVB_OK;
+}
+
+int uvb_get_knob(int knob) {
+  if (knob < 0 || knob >= UVB_KNOB_COUNT) return fail(UVB_ERR_INVALID, "unknown knob %d", knob);
+  return g_knobs[knob];
+}
 
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
@@ -689,20 +754,12 @@ int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, in
   p.N = N;
   p.K = K;
   p.act = act;
-  // Tuning hooks (read once): UVB_GEMM_CTAS=1 keeps one CTA per tile instead of CTA pairs (cta_group::2);
-  // UVB_GEMM_BN=192|256 pins the tile width
-  static const int ctas = [] {
-    const char* e = getenv("UVB_GEMM_CTAS");
-    return e != nullptr && atoi(e) == 1 ? 1 : 2;
-  }();
+  const int ctas = g_knobs[UVB_KNOB_GEMM_CTAS] == 1 ? 1 : 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int workers = 0;
   // Small problems (the 512 context rows of the cross-attention k / v projections, single-row probes): when 128 x 64
   // tiles of single CTAs fit in ONE wave, latency is what counts -- many small tiles instead of a dozen 256-wide pairs.
-  static const bool allow_small = [] {
-    const char* e = getenv("UVB_GEMM_SMALL");
-    return e == nullptr || atoi(e) != 0;
-  }();
+  const bool allow_small = g_knobs[UVB_KNOB_GEMM_SMALL] != 0;
   const long long small_tiles = static_cast<long long>((M + uvb::kGemmBM - 1) / uvb::kGemmBM) * ((N + 63) / 64);
   if (allow_small && small_tiles <= sms) return launch_gemm<1, 64>(p, x, w, y, ldx, ldw, ldy, sms, st);
   if (ctas == 2) {

@@ -29,6 +29,17 @@
 // on it.  K/V tiles (128 keys x 128 dims) alternate through one TMA ring; Q stays resident in smem for the
 // segment and its buffer is reused to stage O for the TMA store.
 //
+// CTA pairs (kCtas == 2, long key sequences): a cluster of two CTAs on one TPC works on a 512-row unit -- CTA r
+// owns query rows [q0 + 256 r, +256) as its two tiles -- and every MMA is one tcgen05.mma.cta_group::2 with M = 256
+// covering tile t of BOTH CTAs, issued by the leader's warp 8.  Each CTA stages only HALF of every K tile (64 of
+// the 128 keys: the N split of Q K^T) and HALF of every V tile (64 of the 128 dims: the N split of P V), so the
+// tensor core of an SM reads 80 KiB instead of 112 KiB of shared memory per (query tile, key tile) and TMA writes
+// 16 KiB instead of 32 KiB: 109 B/clk against the 128 B/clk an SM delivers (156 B/clk single-CTA, i.e. over the
+// limit).  TMA loads of both CTAs count on the LEADER's q_full / kv_full barriers (cp.async.bulk.tensor
+// .cta_group::2); s_full / pv_done / o_full / kv_empty are multicast commits that arrive in both CTAs; p_full lives
+// in the leader and collects the 4 + 4 softmax warps of both CTAs (remote mbarrier.arrive.release.cluster).
+// Softmax, lazy rescale, epilogue, stream-K partials and peer-rank stores stay per CTA; the schedule runs over pairs.
+//
 // Ordering facts the protocol relies on: tcgen05 MMAs issued by one thread execute in order, so
 // S_t(s+1) overwriting the buffer that held P_t(s) is safe once PV_t(s) has been issued before it; the
 // softmax warps rescale O_t in place (lazily, only when a row max grows by more than 2^8) after waiting
@@ -59,14 +70,16 @@ constexpr int kWsSlotFloats = kWsOFloats + 2 * kUnitRows;
 // kStages K/V ring slots, kQBufs query-block buffers.  Self-attention (hundreds of key tiles per query
 // block) uses <4, 1>; cross-attention (4 key tiles per query block) uses <3, 2>: the next block's Q is
 // prefetched while the current one is computed and its O tile drains through the other buffer.
-template <int kStages, int kQBufs>
+template <int kStages, int kQBufs, int kCtas = 1>
 struct FmhaSmem {
+  static_assert(kCtas == 1 || (kCtas == 2 && kQBufs == 1), "CTA pairs exist for the long-key variant only");
+  static constexpr int kStageBytes = kTileBytes / kCtas;   // a pair CTA stages half of every K / V tile
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQBufs * kQTiles * kTileBytes;
   // kQBufs == 1 (long key sequences): the second 64-key half of P goes through shared memory (16 KiB per query
   // tile, K-major SWIZZLE_128B like Q) so that the next score tile can be issued before it is consumed
   static constexpr bool kPSmem = kQBufs == 1;
-  static constexpr int kPOff = kKvOff + kStages * kTileBytes;
+  static constexpr int kPOff = kKvOff + kStages * kStageBytes;
   static constexpr int kBarOff = kPOff + (kPSmem ? kQTiles * kHalfTile : 0);
   // barriers: q_full[B][2] q_empty[B][2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
   static constexpr int kNumBars = 4 * kQBufs + 2 * kStages + 10;
@@ -77,6 +90,7 @@ struct FmhaSmem {
 struct FmhaParams {
   CUtensorMap tm_q;   // dims (d, token, head, batch), box (64, 128, 1, 1), SWIZZLE_128B
   CUtensorMap tm_k;
+  CUtensorMap tm_kh;  // same tensor as tm_k, box (64, 64, 1, 1): the 64-key half a pair CTA stages
   CUtensorMap tm_v;
   CUtensorMap tm_o;
   const int* k_lens;              // [B] or nullptr (= Lk)
@@ -97,7 +111,7 @@ struct FmhaParams {
   CUtensorMap tm_o_peer[8];
   int Lq;
   int Lk;
-  int n_qt;                       // 256-row query blocks per (batch, head)
+  int n_qt;                       // query blocks (256 rows, 512 for CTA pairs) per (batch, head)
   int N;                          // heads
   int n_units;                    // B * N * n_qt
   float scale_log2;               // softmax_scale * log2(e)
@@ -118,9 +132,10 @@ struct FmhaSched {
 
   __device__ __forceinline__ long long rem_lo(int cta) const { return rem_total * cta / G; }
 
-  __device__ __forceinline__ void init(const FmhaParams& p, bool split) {
-    G = static_cast<int>(gridDim.x);
-    g = static_cast<int>(blockIdx.x);
+  // n_workers CTAs (or CTA pairs) walk the unit list; `worker` is this CTA's (pair's) index
+  __device__ __forceinline__ void init(const FmhaParams& p, bool split, int n_workers, int worker) {
+    G = n_workers;
+    g = worker;
     n_kv = (p.Lk + kBlockN - 1) / kBlockN;
     W = p.n_units / G;
     const int R = p.n_units - W * G;
@@ -160,7 +175,13 @@ struct FmhaSched {
 // kPolyEvery goes through the FMA-pipe polynomial instead of MUFU.EX2 (0 = never): the XU pipe does 16
 // exp2/clk/SM, exactly the rate at which the tensor pipe consumes a 128x128 tile, so offloading a share
 // of them is what lets the softmax keep ahead of the MMAs.
-template <int kPairs, int kPolyEvery, bool kKeyMod>
+// Lab builds only (-DUVB_FMHA_POLY_EVERY=n): one exp2 pair in every n goes through the FMA-pipe polynomial.
+#ifndef UVB_FMHA_POLY_EVERY
+#define UVB_FMHA_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = UVB_FMHA_POLY_EVERY;
+
+template <int kPairs, bool kKeyMod>
 __device__ __forceinline__ void softmax_exp(const uint32_t* sr, float scale_log2, float neg_ms,
                                             float2& sum_a, float2& sum_b, uint32_t* pk,
                                             const float* pvw) {
@@ -191,10 +212,11 @@ __device__ __forceinline__ void softmax_exp(const uint32_t* sr, float scale_log2
   }
 }
 
-template <int kStages, int kQBufs, int kPolyEvery, bool kKeyMod>
+template <int kStages, int kQBufs, int kCtas, bool kKeyMod>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
-  using SM = FmhaSmem<kStages, kQBufs>;
+  using SM = FmhaSmem<kStages, kQBufs, kCtas>;
+  constexpr int kStageBytes = SM::kStageBytes;
   static_assert(SM::kDynBytes <= 232448, "shared memory budget (227 KiB)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -219,6 +241,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * kQBufs; ++i) {
@@ -227,8 +251,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[2 * t], 4);       // one arrive per softmax warp
-      mbar_init(&p_full[2 * t + 1], 4);
+      mbar_init(&p_full[2 * t], 4 * kCtas);       // one arrive per softmax warp (of both CTAs of a pair)
+      mbar_init(&p_full[2 * t + 1], 4 * kCtas);
       mbar_init(&pv_done[t], 1);
       mbar_init(&o_full[t], 1);
     }
@@ -239,24 +263,35 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     fence_mbar_init();
   }
   if (warp == 8) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if constexpr (kCtas == 2) {
+      tmem_alloc_pair(tmem_ptr, 512);
+    } else {
+      tmem_alloc(tmem_ptr, 512);
+      tmem_relinquish();
+    }
   }
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
-    tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(kCtas == 2 ? &p.tm_kh : &p.tm_k);
     tma_prefetch_desc(&p.tm_v);
     if (p.n_peers == 0) tma_prefetch_desc(&p.tm_o);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();     // the peer's barriers are initialised and its TMEM is allocated
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   // warp-uniform copy (a plain smem load is not provably uniform and would force ptxas to wrap every
   // tcgen05 instruction in an R2UR.BROADCAST waterfall loop)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   FmhaSched sch;
-  sch.init(p, p.ws != nullptr);
+  sch.init(p, p.ws != nullptr, static_cast<int>(gridDim.x) / kCtas, static_cast<int>(blockIdx.x) / kCtas);
+  // stream-K workspace slots and flags are per CTA: CTA r of pair g exchanges partials with CTA r of other pairs
+  const int my_slot = static_cast<int>(blockIdx.x);
+  auto slot_of = [&](int worker) { return worker * kCtas + static_cast<int>(cta_rank); };
 
   // (batch, head, first query row) of a unit and its key-tile range clipped to the batch's key length
   auto decode = [&](const FmhaSeg& sg, int& batch, int& head, int& q_row0, int& k_len, int& ka, int& kb) {
@@ -264,7 +299,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     const int bh = sg.unit / p.n_qt;
     head = bh % p.N;
     batch = bh / p.N;
-    q_row0 = qt * kUnitRows;
+    q_row0 = (qt * kCtas + static_cast<int>(cta_rank)) * kUnitRows;
     k_len = p.Lk;
     if (p.k_lens != nullptr) k_len = min(max(__ldg(p.k_lens + batch), 0), p.Lk);
     const int n_kv_b = (k_len + kBlockN - 1) / kBlockN;
@@ -278,6 +313,9 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       // ===================================== TMA producer =====================================
       // the whole warp runs the loop (converged, uniform operands); one elected lane issues
       int ring = 0;
+      // pair: both CTAs' loads report to the LEADER's full barriers (cluster addresses)
+      const uint32_t q_full_cl = kCtas == 2 ? map_to_cta(&q_full[0], 0) : 0u;
+      const uint32_t kv_full_cl = kCtas == 2 ? map_to_cta(&kv_full[0], 0) : 0u;
       for (int si = 0; si < sch.n_seg; ++si) {
         const FmhaSeg sg = sch.seg(si);
         int batch, head, q_row0, k_len, ka, kb;
@@ -289,9 +327,16 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           mbar_wait(&q_empty[2 * qb + t], qpar ^ 1);
           uint8_t* dst = smem_q + (2 * qb + t) * kTileBytes;
           if (elect_one()) {
-            mbar_arrive_expect_tx(full, kTileBytes);
-            tma_load_4d_hint(dst, &p.tm_q, full, 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
-            tma_load_4d_hint(dst + kHalfTile, &p.tm_q, full, 64, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+            if constexpr (kCtas == 2) {
+              if (leader) mbar_arrive_expect_tx(full, 2 * kTileBytes);
+              const uint32_t fb = q_full_cl + (2 * qb + t) * 8;
+              tma_load_4d_pair(dst, &p.tm_q, fb, 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+              tma_load_4d_pair(dst + kHalfTile, &p.tm_q, fb, 64, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+            } else {
+              mbar_arrive_expect_tx(full, kTileBytes);
+              tma_load_4d_hint(dst, &p.tm_q, full, 0, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+              tma_load_4d_hint(dst + kHalfTile, &p.tm_q, full, 64, q_row0 + t * kBlockM, head, batch, kEvictFirst);
+            }
           }
           __syncwarp();
         }
@@ -299,50 +344,80 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         for (int i = 2 * ka; i < 2 * kb; ++i, ++ring) {
           const int stage = ring % kStages;
           mbar_wait(&kv_empty[stage], ((ring / kStages) & 1) ^ 1);
-          uint8_t* dst = smem_kv + stage * kTileBytes;
-          const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
+          uint8_t* dst = smem_kv + stage * kStageBytes;
           const int key0 = (i >> 1) * kBlockN;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&kv_full[stage], kTileBytes);
-            tma_load_4d_hint(dst, tm, &kv_full[stage], 0, key0, head, batch, kEvictLast);
-            tma_load_4d_hint(dst + kHalfTile, tm, &kv_full[stage], 64, key0, head, batch, kEvictLast);
+            if constexpr (kCtas == 2) {
+              if (leader) mbar_arrive_expect_tx(&kv_full[stage], 2 * kStageBytes);
+              const uint32_t fb = kv_full_cl + stage * 8;
+              if (i & 1) {
+                // V: all 128 keys x this CTA's 64 dims (one panel): the N half of P V
+                tma_load_4d_pair(dst, &p.tm_v, fb, 64 * static_cast<int>(cta_rank), key0, head, batch, kEvictLast);
+              } else {
+                // K: this CTA's 64 keys x 128 dims (two panels of 8 KiB): the N half of Q K^T
+                const int kr = key0 + 64 * static_cast<int>(cta_rank);
+                tma_load_4d_pair(dst, &p.tm_kh, fb, 0, kr, head, batch, kEvictLast);
+                tma_load_4d_pair(dst + kHalfTile / 2, &p.tm_kh, fb, 64, kr, head, batch, kEvictLast);
+              }
+            } else {
+              const CUtensorMap* tm = (i & 1) ? &p.tm_v : &p.tm_k;
+              mbar_arrive_expect_tx(&kv_full[stage], kTileBytes);
+              tma_load_4d_hint(dst, tm, &kv_full[stage], 0, key0, head, batch, kEvictLast);
+              tma_load_4d_hint(dst + kHalfTile, tm, &kv_full[stage], 64, key0, head, batch, kEvictLast);
+            }
           }
           __syncwarp();
         }
       }
-    } else if (warp == 8) {
-      // ===================================== MMA issuer =======================================
+    } else if (warp == 8 && leader) {
+      // ===================================== MMA issuer (pair: leader CTA only) ===============
       // The whole warp runs the control flow converged so every operand is warp-uniform; one elected
       // lane (always the same one) issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are
       // built once; per instruction only a 64-bit add of a compile-time offset remains.  (Round-1 ncu:
       // with the loop inside `if (lane == 0)` ptxas emitted an ELECT/R2UR.BROADCAST waterfall around each
       // UTCHMMA and descriptor math on the uniform datapath -- ~110 cycles per MMA, the real bottleneck.)
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM * kCtas, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM * kCtas, kHeadDim, 0, 1);
       const uint64_t q_desc = umma_desc_sw128(smem_u32(smem_q), 16, 1024);            // K-major A
       const uint64_t k_desc = umma_desc_sw128(smem_u32(smem_kv), 16, 1024);           // K-major B
       const uint64_t v_desc = umma_desc_sw128(smem_u32(smem_kv), kHalfTile, 1024);    // MN-major B
       constexpr uint64_t kTile16 = kTileBytes >> 4;           // descriptor address units are 16 B
+      constexpr uint64_t kStage16 = kStageBytes >> 4;
+      constexpr int kKPanel = kHalfTile / kCtas;              // bytes of one 64-dim panel of the staged K rows
+      auto mma_ss = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if constexpr (kCtas == 2) umma_ss_pair(d, a, b, idesc, acc); else umma_ss(d, a, b, idesc, acc);
+      };
+      auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if constexpr (kCtas == 2) umma_ts_pair(d, a, b, idesc, acc); else umma_ts(d, a, b, idesc, acc);
+      };
+      // p_full collects remote arrives of the peer CTA's softmax warps: acquire at cluster scope
+      auto wait_p = [&](uint64_t* bar, uint32_t par) {
+        if constexpr (kCtas == 2) mbar_wait_cluster(bar, par); else mbar_wait(bar, par);
+        tc_fence_after();
+      };
 
       auto wait_full = [&](int r) {
         mbar_wait(&kv_full[r % kStages], (r / kStages) & 1);
         tc_fence_after();
       };
-      auto commit = [&](uint64_t* bar) {
-        if (elect_one()) tc_commit(bar);
+      auto commit = [&](uint64_t* bar) {     // pair: the arrive is multicast to the same barrier of both CTAs
+        if (elect_one()) {
+          if constexpr (kCtas == 2) tc_commit_pair(bar); else tc_commit(bar);
+        }
         __syncwarp();
       };
       // S_t = Q_t K^T : A, B K-major, N = 128 keys; 8 K-steps of 16 dims: panel = kk/4, 32 B per K-step
       // inside the 128 B swizzle atom
       auto issue_qk = [&](int qt, int t, int k_ring) {   // qt = 2 * query buffer + tile
         const uint64_t qa = q_desc + qt * kTile16;
-        const uint64_t ka = k_desc + (k_ring % kStages) * kTile16;
+        const uint64_t ka = k_desc + (k_ring % kStages) * kStage16;
         const uint32_t d = tmem_base + t * 128;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-            const uint64_t off = ((kk >> 2) * kHalfTile + (kk & 3) * 32) >> 4;
-            umma_ss(d, qa + off, ka + off, idesc_qk, kk > 0 ? 1u : 0u);
+            const uint64_t aoff = ((kk >> 2) * kHalfTile + (kk & 3) * 32) >> 4;
+            const uint64_t boff = ((kk >> 2) * kKPanel + (kk & 3) * 32) >> 4;
+            mma_ss(d, qa + aoff, ka + boff, idesc_qk, kk > 0 ? 1u : 0u);
           }
         }
         __syncwarp();
@@ -352,19 +427,19 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       // second half of P from shared memory (kPSmem): A K-major like Q, keys 64..127 of the V tile
       const uint64_t p_desc = umma_desc_sw128(smem_u32(smem_p), 16, 1024);
       auto issue_pv_smem = [&](int t, int v_ring) {
-        const uint64_t va = v_desc + (v_ring % kStages) * kTile16;
+        const uint64_t va = v_desc + (v_ring % kStages) * kStage16;
         const uint64_t pa = p_desc + t * (kHalfTile >> 4);
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
         if (elect_one()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            umma_ss(d, pa + ((k4 * 32) >> 4), va + (4 + k4) * (2048 >> 4), idesc_pv, 1u);
+            mma_ss(d, pa + ((k4 * 32) >> 4), va + (4 + k4) * (2048 >> 4), idesc_pv, 1u);
           }
         }
         __syncwarp();
       };
       auto issue_pv = [&](int t, int v_ring, bool first_step, int kk0) {   // 4 K-steps = 64 keys from kk0
-        const uint64_t va = v_desc + (v_ring % kStages) * kTile16;
+        const uint64_t va = v_desc + (v_ring % kStages) * kStage16;
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
         const uint32_t a = tmem_base + t * 128;
         const uint32_t acc0 = (!first_step || kk0 > 0) ? 1u : 0u;
@@ -372,7 +447,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const int kk = kk0 + k4;
-            umma_ts(d, a + kk * 8, va + kk * (2048 >> 4), idesc_pv, k4 > 0 ? 1u : acc0);
+            mma_ts(d, a + kk * 8, va + kk * (2048 >> 4), idesc_pv, k4 > 0 ? 1u : acc0);
           }
         }
         __syncwarp();
@@ -415,8 +490,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 #pragma unroll
           for (int t = 0; t < kQTiles; ++t) {
             // split-P: the first 64 keys of P_t are signalled while the softmax still works on the rest
-            mbar_wait(&p_full[2 * t + 0], par);
-            tc_fence_after();
+            wait_p(&p_full[2 * t + 0], par);
             issue_pv(t, v_ring, step == 0, 0);
             if constexpr (kPSmem) {
               // The first half of P has arrived, so all of S_t sits in the softmax registers, and the PV just
@@ -429,14 +503,12 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
                 issue_qk(2 * qb + t, t, k_ring);
                 commit(&s_full[t]);
               }
-              mbar_wait(&p_full[2 * t + 1], par);
-              tc_fence_after();
+              wait_p(&p_full[2 * t + 1], par);
               issue_pv_smem(t, v_ring);
               commit(&pv_done[t]);
               if (!more) commit(&o_full[t]);
             } else {
-              mbar_wait(&p_full[2 * t + 1], par);
-              tc_fence_after();
+              wait_p(&p_full[2 * t + 1], par);
               issue_pv(t, v_ring, step == 0, 4);
               commit(&pv_done[t]);
               if (more) {
@@ -466,6 +538,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     const uint32_t tO = tmem_base + lane_addr + 256 + t * kHeadDim;
     const float scale_log2 = p.scale_log2;
     const int ws_row = t * kBlockM + row;          // row inside the unit
+    // pair: p_full lives in the leader CTA
+    const uint32_t p_full_cl = kCtas == 2 ? map_to_cta(&p_full[0], 0) : 0u;
     bool stored = false;
     int pending_qb = -1;   // kQBufs == 2: query buffer whose O store was issued but not yet released
     int gstep = 0;
@@ -582,7 +656,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             // takes ~230 cycles per step off this warp but adds as much to the hand-off latency of the last
             // PV, which is on the dependency chain: measured slower.)
             uint32_t pk[32];
-            softmax_exp<32, kPolyEvery, kKeyMod>(sr + 64, scale_log2, neg_ms, sum_a, sum_b, pk,
+            softmax_exp<32, kKeyMod>(sr + 64, scale_log2, neg_ms, sum_a, sum_b, pk,
                                                  pvw == nullptr ? nullptr : pvw + 64);
             if (gstep + step > 0) mbar_wait(&pv_done[t], par ^ 1);
             uint8_t* prow = smem_p + t * kHalfTile + row * 128;
@@ -594,14 +668,20 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             fence_proxy_async_smem();
           } else {
             uint32_t pk[32];
-            softmax_exp<32, kPolyEvery, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
+            softmax_exp<32, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
                                                  pvw == nullptr ? nullptr : pvw + 64 * h);
             tmem_st_x32(tS + 32 * h, pk);
             tmem_wait_st();
             tc_fence_before();
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[2 * t + h]);   // one barrier per 64-key half (split-P)
+          if (lane == 0) {                                   // one barrier per 64-key half (split-P)
+            if constexpr (kCtas == 2) {
+              mbar_arrive_cluster(p_full_cl + (2 * t + h) * 8);
+            } else {
+              mbar_arrive(&p_full[2 * t + h]);
+            }
+          }
         }
         l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
         if constexpr (kQBufs == 2) {
@@ -618,7 +698,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
       if (!sg.owner) {
         // ---- partial: un-normalised O (fp32, column-major so a warp writes 128 contiguous bytes), m, l
-        float* slot = p.ws + static_cast<size_t>(sch.g) * kWsSlotFloats;
+        float* slot = p.ws + static_cast<size_t>(my_slot) * kWsSlotFloats;
         if (have_o) {
 #pragma unroll
           for (int c = 0; c < kHeadDim / 32; ++c) {
@@ -635,7 +715,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         tc_fence_before();
         named_bar_sync(1 + t, kBlockM);
         if (wq == 0 && lane == 0) {
-          st_release_gpu(p.flags + 2 * sch.g + t, 1u);
+          st_release_gpu(p.flags + 2 * my_slot + t, 1u);
           mbar_arrive(&q_empty[2 * (si % kQBufs) + t]);
         }
         continue;
@@ -649,14 +729,14 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         while (g_lo > 0 && sch.rem_lo(g_lo) > unit_lo) --g_lo;
         for (int gp = g_lo; gp < sch.g; ++gp) {
           if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;     // that CTA has no remainder range
-          const uint32_t* flag = p.flags + 2 * gp + t;
+          const uint32_t* flag = p.flags + 2 * slot_of(gp) + t;
           if (ld_acquire_gpu(flag) == 0u) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(flag) == 0u) {
               if (clock64() - t0 > 8000000000LL) __trap();
             }
           }
-          const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+          const float* slot = p.ws + static_cast<size_t>(slot_of(gp)) * kWsSlotFloats;
           if (__ldcg(slot + kWsOFloats + kUnitRows + ws_row) > 0.f)
             m_tot = fmaxf(m_tot, __ldcg(slot + kWsOFloats + ws_row));
         }
@@ -666,7 +746,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       if (sg.a > 0) {
         for (int gp = g_lo; gp < sch.g; ++gp) {
           if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;
-          const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+          const float* slot = p.ws + static_cast<size_t>(slot_of(gp)) * kWsSlotFloats;
           const float lp = __ldcg(slot + kWsOFloats + kUnitRows + ws_row);
           if (lp > 0.f) l_tot += lp * ex2_approx((__ldcg(slot + kWsOFloats + ws_row) - m_tot) * scale_log2);
         }
@@ -709,7 +789,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         if (sg.a > 0) {
           for (int gp = g_lo; gp < sch.g; ++gp) {
             if (sch.rem_lo(gp + 1) == sch.rem_lo(gp)) continue;
-            const float* slot = p.ws + static_cast<size_t>(gp) * kWsSlotFloats;
+            const float* slot = p.ws + static_cast<size_t>(slot_of(gp)) * kWsSlotFloats;
             const float lp = __ldcg(slot + kWsOFloats + kUnitRows + ws_row);
             if (lp > 0.f) {
               const float w = ex2_approx((__ldcg(slot + kWsOFloats + ws_row) - m_tot) * scale_log2) * inv;
@@ -777,7 +857,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         tma_store_commit();
         if (sg.a > 0) {   // every thread of the group has read the partials: hand the slots back
           for (int gp = g_lo; gp < sch.g; ++gp) {
-            if (sch.rem_lo(gp + 1) != sch.rem_lo(gp)) st_release_gpu(p.flags + 2 * gp + t, 0u);
+            if (sch.rem_lo(gp + 1) != sch.rem_lo(gp)) st_release_gpu(p.flags + 2 * slot_of(gp) + t, 0u);
           }
         }
         if constexpr (kQBufs == 2) {
@@ -797,10 +877,18 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
   // ------------------------------------------ teardown ------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();     // the leader's MMAs read the peer's shared memory / TMEM until the very end
+  } else {
+    __syncthreads();
+  }
   if (warp == 8) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (kCtas == 2) {
+      tmem_dealloc_pair(tmem_base, 512);
+    } else {
+      tmem_dealloc(tmem_base, 512);
+    }
   }
 }
 

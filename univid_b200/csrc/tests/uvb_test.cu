@@ -197,7 +197,7 @@ static int run_fmha(int argc, char** argv) {
     if (!ok) {
       // error map by 128x? blocks to localise descriptor/layout mistakes
       printf("  per-(qtile,dpanel) max err for b=0,n=0:\n");
-      for (int qt = 0; qt < (Lq + 127) / 128 && qt < 6; ++qt) {
+      for (int qt = 0; qt < (Lq + 127) / 128 && qt < 12; ++qt) {
         printf("   qtile %d:", qt);
         for (int dp = 0; dp < 8; ++dp) {
           double mx = 0;
@@ -570,11 +570,34 @@ static int run_gemm(int argc, char** argv) {
   return status;
 }
 
+// UVB_KNOBS="fmha_pair=0,gemm_ctas=1": the TEST binary maps its environment onto uvb_set_knob (the library itself
+// never reads the environment)
+static void apply_knobs() {
+  const char* e = getenv("UVB_KNOBS");
+  if (e == nullptr) return;
+  static const char* names[UVB_KNOB_COUNT] = {"fmha_pair", "fmha_split", "gemm_ctas", "gemm_bn", "gemm_small",
+                                              "prologue_pair"};
+  std::vector<char> buf(e, e + strlen(e) + 1);
+  for (char* tok = strtok(buf.data(), ","); tok != nullptr; tok = strtok(nullptr, ",")) {
+    char* eq = strchr(tok, '=');
+    if (eq == nullptr) continue;
+    *eq = 0;
+    int found = -1;
+    for (int i = 0; i < UVB_KNOB_COUNT; ++i)
+      if (!strcmp(tok, names[i])) found = i;
+    if (found < 0 || uvb_set_knob(found, atoi(eq + 1)) != 0) {
+      printf("bad knob '%s'\n", tok);
+      exit(2);
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("usage: uvb_test fmha|prol|gemm ...\n");
     return 2;
   }
+  apply_knobs();
   if (!strcmp(argv[1], "fmha")) return run_fmha(argc, argv);
   if (!strcmp(argv[1], "prol")) return run_prol(argc, argv);
   if (!strcmp(argv[1], "gemm")) return run_gemm(argc, argv);
