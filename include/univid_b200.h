@@ -43,13 +43,15 @@ const char* uvb_last_error(void);
  * returns the value (>= 0) or UVB_ERR_INVALID.  (No reference counterpart: the reference selects its
  * attention backend with module-level flags, attention.py:4-17.) */
 enum uvb_knob {
-  UVB_KNOB_FMHA_PAIR = 0,     /* 1: CTA-pair (cta_group::2) attention kernel for Lk > 2048 (default); 0: single CTAs */
+  UVB_KNOB_FMHA_PAIR = 0,     /* 1: CTA-pair (cta_group::2) attention kernel for Lk > 2048 (default); 0: single CTAs
+                                 (2: pairs with early S release -- lab builds only, -DUVB_LAB_VARIANTS) */
   UVB_KNOB_FMHA_SPLIT = 1,    /* 1: stream-K split of the remainder query blocks (default); 0: never split */
   UVB_KNOB_GEMM_CTAS = 2,     /* 2: CTA-pair GEMM tiles (default); 1: single-CTA tiles */
   UVB_KNOB_GEMM_BN = 3,       /* 0: tile width chosen per problem (default); 192 | 256: pinned */
   UVB_KNOB_GEMM_SMALL = 4,    /* 1: one-wave 128x64 tiles for small problems (default); 0: off */
   UVB_KNOB_PROLOGUE_PAIR = 5, /* 1: token-pair q/k prologue kernel (default); 0: one row per warp group */
-  UVB_KNOB_COUNT = 6
+  UVB_KNOB_FMHA_POLY = 6,     /* lab builds only: one exp2 pair in every n (2, 3, 4) on the FMA pipe; 0 (default, shipped) = MUFU only */
+  UVB_KNOB_COUNT = 7
 };
 int uvb_set_knob(int knob, int value);
 int uvb_get_knob(int knob);

@@ -1,8 +1,9 @@
-"""Load the UNMODIFIED reference hot-path sources from /root/reference -- TEST INFRASTRUCTURE.
+"""Load the UNMODIFIED reference hot-path sources -- TEST INFRASTRUCTURE.
 
-Used only in the build container (the GPU box has no /root/reference) by
-tests/golden/make_golden.py and tests/test_oracle_vs_reference.py to pin the oracle.  Nothing is
-copied: the files are imported from where they lie (recipe: SURVEY.md sec. 8c).
+From /root/reference when it is mounted (the build container: tests/golden/make_*.py, tests/test_reference_compat.py
+pin the oracle with it), otherwise from oracle/_ref/, the byte-for-byte staging of the same files that
+oracle/make_ref.py writes (git-ignored; it travels to the GPU box like a built .so, where bench.py's reference arm and
+tests/test_reference_binding_gpu.py use it).  The files are imported as they are (recipe: SURVEY.md sec. 8c).
 
   * a 4-symbol stub stands in for `diffusers` (only ConfigMixin / register_to_config / ModelMixin are
     used, model.py:6-7);
@@ -24,7 +25,20 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("UNIVID_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")          # written by oracle/make_ref.py (git-ignored, travels to the GPU box)
+
+
+def _pick_root():
+    env = os.environ.get("UNIVID_REFERENCE")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/models/wan/utils/modules/model.py"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REF_ROOT = _pick_root()
 MODULES_DIR = os.path.join(REF_ROOT, "models/wan/utils/modules")
 DIST_DIR = os.path.join(REF_ROOT, "models/wan/distributed")
 PIPELINE = os.path.join(REF_ROOT, "models/model_pipeline.py")

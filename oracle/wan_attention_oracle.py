@@ -288,6 +288,56 @@ def attention_block(x, e, prm, seq_lens, grid_sizes, freqs, context, context_len
     return x + y * m[5]                                                                    # :257
 
 
+# ------------------------------------------------------------------------------------------------
+# WanModel.forward -- model.py:410-497 (patchify + pad, time / text embeddings, blocks, head, unpatchify)
+# ------------------------------------------------------------------------------------------------
+def sinusoidal_embedding_1d(dim, position):
+    """cos | sin of position * 10000^(-i / half), float64 (model.py:13-24)."""
+    half = dim // 2
+    pos = position.to(torch.float64)
+    ang = torch.outer(pos, torch.pow(10000, -torch.arange(half).to(pos).div(half)))
+    return torch.cat([torch.cos(ang), torch.sin(ang)], dim=1)
+
+
+def dit_forward(lat, t, ctx, prm, seq_len, num_heads, num_layers, dim, freq_dim, text_len, out_dim,
+                patch_size=(1, 2, 2), eps=1e-6, bf16=False, route="sdpa"):
+    """WanModel.forward (model.py:410-497) for model_type 't2v' / 'ti2v' (no y).  prm = the model's state dict.
+    lat: list of [C_in, F, H, W]; t: [B] (B == 1 only, like the reference's expand at :461) or [B, seq_len];
+    ctx: list of [L, text_dim].  fp32 evaluation by default (bf16=False: the 'fp32 reference' of the tolerance)."""
+    freqs = make_freqs(dim // num_heads)
+    xs = [F.conv3d(u.unsqueeze(0), prm["patch_embedding.weight"], prm["patch_embedding.bias"], stride=patch_size)
+          for u in lat]                                                                              # :445
+    grid_sizes = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in xs])               # :446-447
+    xs = [u.flatten(2).transpose(1, 2) for u in xs]
+    seq_lens = torch.tensor([u.size(1) for u in xs], dtype=torch.long)
+    assert int(seq_lens.max()) <= seq_len
+    x = torch.cat([torch.cat([u, u.new_zeros(1, seq_len - u.size(1), u.size(2))], dim=1) for u in xs])  # :451-454
+    if t.dim() == 1:
+        t = t.expand(t.size(0), seq_len)                                                              # :460-461
+    bt = t.size(0)
+    emb = sinusoidal_embedding_1d(freq_dim, t.flatten()).unflatten(0, (bt, seq_len)).float()          # :465-467
+    e = F.linear(F.silu(F.linear(emb, prm["time_embedding.0.weight"], prm["time_embedding.0.bias"])),
+                 prm["time_embedding.2.weight"], prm["time_embedding.2.bias"])
+    e0 = F.linear(F.silu(e), prm["time_projection.1.weight"], prm["time_projection.1.bias"]).unflatten(2, (6, dim))
+    c = torch.stack([torch.cat([u, u.new_zeros(text_len - u.size(0), u.size(1))]) for u in ctx])      # :473-478
+    c = _linear(F.gelu(_linear(c, prm["text_embedding.0.weight"], prm["text_embedding.0.bias"], bf16),
+                       approximate="tanh"), prm["text_embedding.2.weight"], prm["text_embedding.2.bias"], bf16)
+    for i in range(num_layers):
+        pre = f"blocks.{i}."
+        blk = {k[len(pre):]: v for k, v in prm.items() if k.startswith(pre)}
+        x = attention_block(x, e0, blk, seq_lens, grid_sizes, freqs, c, None, num_heads, eps, bf16, route,
+                            cross_attn_norm="norm3.weight" in blk)
+    m = (prm["head.modulation"].unsqueeze(0) + e.unsqueeze(2)).chunk(2, dim=2)                         # Head.forward :286
+    h = layer_norm(x, eps) * (1 + m[1].squeeze(2)) + m[0].squeeze(2)
+    y = F.linear(h.float(), prm["head.head.weight"], prm["head.head.bias"])                            # fp32 autocast region
+    out = []
+    for u, v in zip(y, grid_sizes.tolist()):                                                           # unpatchify :516-521
+        u = u[:math.prod(v)].view(*v, *patch_size, out_dim)
+        u = torch.einsum("fhwpqrc->cfphqwr", u)
+        out.append(u.reshape(out_dim, *[i * j for i, j in zip(v, patch_size)]).float())
+    return out
+
+
 def init_block_params(dim, ffn_dim, generator, realistic_bias=True):
     """State dict of one WanAttentionBlock (cross_attn_norm=True) with the init rules of SURVEY.md sec. 8d."""
     prm = {"modulation": torch.randn(1, 6, dim, generator=generator) / dim ** 0.5}

@@ -266,7 +266,12 @@ def test_sp_kernels_with_local_peers(ext, p, s, heads, batch):
     torch.cuda.synchronize()
     got = torch.cat(o_recv, dim=1)                                   # [B, L, N, 128]
     assert torch.isfinite(got.float()).all(), "an output row was not written"
-    assert torch.equal(got, o_ref)
+    if L <= 2048:
+        assert torch.equal(got, o_ref)
+    else:
+        # long key sequences split the remainder units over the key axis (stream-K); the split points depend on the
+        # number of heads in the launch, so the per-rank launches merge their partials in a different order
+        assert (got.float() - o_ref.float()).abs().max().item() <= 4e-3
 
 
 @pytest.mark.parametrize("b,lq,lk,n,lens", [(1, 1950, 1950, 12, None), (2, 700, 2300, 3, [2300, 130]), (1, 40000, 512, 5, None),

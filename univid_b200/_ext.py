@@ -19,7 +19,8 @@ EXPORTS = (
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step", "uvb_set_knob", "uvb_get_knob",
 )
 ABI_VERSION = 108
-KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5}
+KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
+         "fmha_poly": 6}
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes

@@ -67,6 +67,27 @@ def build(force=False, verbose=False, with_tests=True):
     return LIB
 
 
+def build_profile_variant(verbose=False):
+    """Lab build (not shipped, not loaded by the package): the library and the stand-alone test binary with
+    -DUVB_FMHA_PROFILE (barrier-wait cycle counters in the attention kernel) and -DUVB_LAB_VARIANTS (the measured and
+    rejected kernel variants: early S release, FMA-pipe exp2) as csrc/tests/prof/."""
+    nvcc = _nvcc()
+    out = os.path.join(CSRC, "tests", "prof")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libunivid_b200.so")
+    for cmd in ([nvcc] + NVCC_FLAGS + ["-DUVB_FMHA_PROFILE", "-DUVB_LAB_VARIANTS", "-shared", "-o", lib, os.path.join(CSRC, "c_api.cu")],
+                [nvcc] + NVCC_FLAGS + ["-DUVB_FMHA_PROFILE", "-o", os.path.join(out, "uvb_test"),
+                                       os.path.join(CSRC, "tests", "uvb_test.cu"), "-L", out, "-lunivid_b200",
+                                       "-Xlinker", "-rpath=$ORIGIN"]):
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
+
+
 if __name__ == "__main__":
+    if "--profile" in sys.argv:
+        print("built", build_profile_variant(verbose=True))
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose=True)
     print("built", LIB)

@@ -61,6 +61,7 @@ int g_knobs[UVB_KNOB_COUNT] = {
     /* UVB_KNOB_GEMM_BN       */ 0,   // 0 = per-problem choice, 192 | 256 pins the tile width
     /* UVB_KNOB_GEMM_SMALL    */ 1,   // single-wave 128x64 tiles for small problems
     /* UVB_KNOB_PROLOGUE_PAIR */ 1,   // token-pair prologue kernel when q and k are both given
+    /* UVB_KNOB_FMHA_POLY     */ 0,   // CTA-pair attention kernel: 1 exp2 pair in every n on the FMA pipe (0, 2, 3, 4)
 };
 
 int check_device() {
@@ -227,6 +228,7 @@ int pick_tile_n(const uvb::GemmParams& p, int workers) {
 }
 
 unsigned long long* g_timeline = nullptr;   // diagnostics: see uvb_debug_fmha_timeline
+unsigned long long* g_prof = nullptr;       // UVB_FMHA_PROFILE lab builds: see uvb_debug_fmha_profile
 
 constexpr int kShortKeyTiles = 16;   // <= 2048 keys: query-block-pipelined variant
 constexpr size_t kWsFlagBytes = 4096;   // flags [sms][2] u32 live at the start of the workspace
@@ -247,17 +249,21 @@ size_t fmha_ws_bytes(int sms) {
   return kWsFlagBytes + static_cast<size_t>(sms) * uvb::kWsSlotFloats * sizeof(float);
 }
 
-constexpr int kPairStages = 8;       // K/V ring slots of 16 KiB in the CTA-pair attention kernel
+// K/V ring slots of 16 KiB in the CTA-pair attention kernels: 8 when half of P stays in TMEM, 6 when both halves of
+// P go through shared memory (kEarlyS: two more 16 KiB panels per query tile)
+template <bool kEarlyS>
+constexpr int pair_stages() { return kEarlyS ? 6 : 8; }
 
 // CTA pairs of the attention kernel the device can hold at once (one per TPC); also sets the kernel's
 // shared-memory attribute for the current device.  0 pairs = fall back to single CTAs.
+template <bool kEarlyS>
 int fmha_pair_workers(int sms, int* out) {
   static int cached_dev = -1, cached = 0;
   int dev = 0;
   UVB_CUDA(cudaGetDevice(&dev));
   if (dev != cached_dev) {
-    using SM = uvb::FmhaSmem<kPairStages, 1, 2>;
-    auto kern = uvb::fmha_fwd_kernel<kPairStages, 1, 2, false>;
+    using SM = uvb::FmhaSmem<pair_stages<kEarlyS>(), 1, 2, kEarlyS>;
+    auto kern = uvb::fmha_fwd_kernel<pair_stages<kEarlyS>(), 1, 2, false, kEarlyS>;
     UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -336,8 +342,23 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   // (cta_group::2: 512-row units, half of every K / V tile per CTA).
   const bool short_keys = n_kv <= kShortKeyTiles;
   int pairs = 0;
-  if (!short_keys && !kKeyMod && g_knobs[UVB_KNOB_FMHA_PAIR] != 0) {
-    if ((rc = fmha_pair_workers(sms, &pairs)) != UVB_OK) return rc;
+  const int pair_mode = g_knobs[UVB_KNOB_FMHA_PAIR];       // 0 single CTAs, 1 pairs, 2 pairs with early S release
+  if (!short_keys && !kKeyMod && pair_mode != 0) {
+#ifdef UVB_LAB_VARIANTS
+    if (pair_mode == 2) {
+      if ((rc = fmha_pair_workers<true>(sms, &pairs)) != UVB_OK) return rc;
+    } else
+#endif
+    {
+      if (pair_mode != 1 || g_knobs[UVB_KNOB_FMHA_POLY] != 0) {
+#ifndef UVB_LAB_VARIANTS
+        return fail(UVB_ERR_UNSUPPORTED, "UVB_KNOB_FMHA_PAIR=%d / UVB_KNOB_FMHA_POLY=%d are lab variants (measured and "
+                    "rejected, DESIGN.md sec. 4 S); build with -DUVB_LAB_VARIANTS to run them", pair_mode,
+                    g_knobs[UVB_KNOB_FMHA_POLY]);
+#endif
+      }
+      if ((rc = fmha_pair_workers<false>(sms, &pairs)) != UVB_OK) return rc;
+    }
   }
   const bool pair = pairs > 0;
   const int unit_rows = uvb::kUnitRows * (pair ? 2 : 1);
@@ -348,6 +369,7 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   p.n_units = static_cast<int>(units);
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timeline = g_timeline;
+  p.prof = g_prof;
 
   // Persistent grid: one CTA per SM; with a workspace the remainder units are cut into equal key ranges
   // (then even fewer units than SMs keep every SM busy).
@@ -372,8 +394,6 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   if (pair) {
-    auto kern = uvb::fmha_fwd_kernel<kPairStages, 1, 2, false>;
-    cfg.dynamicSmemBytes = uvb::FmhaSmem<kPairStages, 1, 2>::kDynBytes;
     cfg.gridDim = dim3(static_cast<unsigned>(2 * grid_w));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -381,7 +401,28 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));      // (max dynamic smem was set by fmha_pair_workers)
+    // (the kernels' max dynamic shared memory was set by fmha_pair_workers)
+#ifdef UVB_LAB_VARIANTS
+    if (pair_mode == 2) {
+      cfg.dynamicSmemBytes = uvb::FmhaSmem<pair_stages<true>(), 1, 2, true>::kDynBytes;
+      UVB_CUDA(cudaLaunchKernelEx(&cfg, uvb::fmha_fwd_kernel<pair_stages<true>(), 1, 2, false, true>, p));
+      return UVB_OK;
+    }
+#endif
+    constexpr int kSt = pair_stages<false>();
+    cfg.dynamicSmemBytes = uvb::FmhaSmem<kSt, 1, 2, false>::kDynBytes;
+    void (*kern)(uvb::FmhaParams) = uvb::fmha_fwd_kernel<kSt, 1, 2, false, false, 0>;
+#ifdef UVB_LAB_VARIANTS
+    switch (g_knobs[UVB_KNOB_FMHA_POLY]) {
+      case 2: kern = uvb::fmha_fwd_kernel<kSt, 1, 2, false, false, 2>; break;
+      case 3: kern = uvb::fmha_fwd_kernel<kSt, 1, 2, false, false, 3>; break;
+      case 4: kern = uvb::fmha_fwd_kernel<kSt, 1, 2, false, false, 4>; break;
+      default: break;
+    }
+    if (g_knobs[UVB_KNOB_FMHA_POLY] != 0)     // the attribute is per instantiation
+      UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.dynamicSmemBytes));
+#endif
+    UVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return UVB_OK;
   }
   void (*kern)(uvb::FmhaParams) = short_keys ? uvb::fmha_fwd_kernel<3, 2, 1, kKeyMod> : uvb::fmha_fwd_kernel<4, 1, 1, kKeyMod>;
@@ -463,6 +504,11 @@ int uvb_get_knob(int knob) {
 void uvb_debug_fmha_timeline(void* device_buffer) {
   g_timeline = static_cast<unsigned long long*>(device_buffer);
 }
+
+#ifdef UVB_FMHA_PROFILE
+// lab builds only (not declared in the public header): per-CTA wait counters, 16 x u64 per CTA
+void uvb_debug_fmha_profile(void* device_buffer) { g_prof = static_cast<unsigned long long*>(device_buffer); }
+#endif
 
 int64_t uvb_fmha_workspace_bytes(void) {
   int sms = 0;

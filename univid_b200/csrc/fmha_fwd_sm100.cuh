@@ -70,9 +70,10 @@ constexpr int kWsSlotFloats = kWsOFloats + 2 * kUnitRows;
 // kStages K/V ring slots, kQBufs query-block buffers.  Self-attention (hundreds of key tiles per query
 // block) uses <4, 1>; cross-attention (4 key tiles per query block) uses <3, 2>: the next block's Q is
 // prefetched while the current one is computed and its O tile drains through the other buffer.
-template <int kStages, int kQBufs, int kCtas = 1>
+template <int kStages, int kQBufs, int kCtas = 1, bool kEarlyS = false>
 struct FmhaSmem {
   static_assert(kCtas == 1 || (kCtas == 2 && kQBufs == 1), "CTA pairs exist for the long-key variant only");
+  static_assert(!kEarlyS || kQBufs == 1, "early S release needs the shared-memory P panels");
   static constexpr int kStageBytes = kTileBytes / kCtas;   // a pair CTA stages half of every K / V tile
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQBufs * kQTiles * kTileBytes;
@@ -80,9 +81,13 @@ struct FmhaSmem {
   // tile, K-major SWIZZLE_128B like Q) so that the next score tile can be issued before it is consumed
   static constexpr bool kPSmem = kQBufs == 1;
   static constexpr int kPOff = kKvOff + kStages * kStageBytes;
-  static constexpr int kBarOff = kPOff + (kPSmem ? kQTiles * kHalfTile : 0);
-  // barriers: q_full[B][2] q_empty[B][2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] + tmem ptr
-  static constexpr int kNumBars = 4 * kQBufs + 2 * kStages + 10;
+  // kEarlyS: BOTH 64-key halves of P go through shared memory (two 16 KiB panels per query tile), nothing of P
+  // aliases S_t any more, and S_t is handed back to the MMA warp as soon as the softmax holds it in registers
+  static constexpr int kPPanels = kPSmem ? (kEarlyS ? 2 : 1) : 0;
+  static constexpr int kBarOff = kPOff + kQTiles * kPPanels * kHalfTile;
+  // barriers: q_full[B][2] q_empty[B][2] kv_full[S] kv_empty[S] s_full[2] p_full[2][2] pv_done[2] o_full[2] s_free[2]
+  // + tmem ptr
+  static constexpr int kNumBars = 4 * kQBufs + 2 * kStages + 12;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for 1024 B alignment
 };
@@ -100,6 +105,7 @@ struct FmhaParams {
   float* ws;                      // [gridDim.x][kWsSlotFloats] or nullptr (then units are never split)
   uint32_t* flags;                // [gridDim.x][2], zero on entry and on exit
   unsigned long long* timeline;   // diagnostics (uvb_debug_fmha_timeline) or nullptr: per CTA 32 x u64
+  unsigned long long* prof;       // UVB_FMHA_PROFILE builds: per CTA 16 x u64 wait counters, or nullptr
   // Fused Ulysses output exchange: when n_peers > 0 the rows [j*chunk, (j+1)*chunk) of the output belong
   // to rank j and are TMA-stored straight into rank j's [B, chunk, N_total, 128] buffer (tm_o_peer[j],
   // mapped over NVLink) at head offset o_head_off; tm_o is unused.
@@ -175,13 +181,21 @@ struct FmhaSched {
 // kPolyEvery goes through the FMA-pipe polynomial instead of MUFU.EX2 (0 = never): the XU pipe does 16
 // exp2/clk/SM, exactly the rate at which the tensor pipe consumes a 128x128 tile, so offloading a share
 // of them is what lets the softmax keep ahead of the MMAs.
-// Lab builds only (-DUVB_FMHA_POLY_EVERY=n): one exp2 pair in every n goes through the FMA-pipe polynomial.
-#ifndef UVB_FMHA_POLY_EVERY
-#define UVB_FMHA_POLY_EVERY 0
+// Lab builds only (-DUVB_FMHA_PROFILE): cycle counters of the barrier waits, per CTA 16 x u64 in FmhaParams::prof
+// [0..2] softmax group 0: total, waiting for S, waiting for PV; [3..5] group 1; [6..10] MMA warp: total, waiting for
+// P half 0, P half 1, K/V tiles, Q; [11] steps
+#ifdef UVB_FMHA_PROFILE
+#define UVB_PROF(acc, stmt)          \
+  do {                               \
+    const long long t0__ = clock64(); \
+    stmt;                            \
+    acc += clock64() - t0__;         \
+  } while (0)
+#else
+#define UVB_PROF(acc, stmt) stmt
 #endif
-constexpr int kPolyEvery = UVB_FMHA_POLY_EVERY;
 
-template <int kPairs, bool kKeyMod>
+template <int kPairs, bool kKeyMod, int kPolyEvery>
 __device__ __forceinline__ void softmax_exp(const uint32_t* sr, float scale_log2, float neg_ms,
                                             float2& sum_a, float2& sum_b, uint32_t* pk,
                                             const float* pvw) {
@@ -212,10 +226,11 @@ __device__ __forceinline__ void softmax_exp(const uint32_t* sr, float scale_log2
   }
 }
 
-template <int kStages, int kQBufs, int kCtas, bool kKeyMod>
+// kPoly: one exp2 pair in every kPoly is evaluated on the FMA pipe instead of MUFU.EX2 (0 = never; UVB_KNOB_FMHA_POLY)
+template <int kStages, int kQBufs, int kCtas, bool kKeyMod, bool kEarlyS = false, int kPoly = 0>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
-  using SM = FmhaSmem<kStages, kQBufs, kCtas>;
+  using SM = FmhaSmem<kStages, kQBufs, kCtas, kEarlyS>;
   constexpr int kStageBytes = SM::kStageBytes;
   static_assert(SM::kDynBytes <= 232448, "shared memory budget (227 KiB)");
   extern __shared__ uint8_t smem_raw[];
@@ -237,7 +252,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   uint64_t* p_full = s_full + 2;                 // [tile][half]
   uint64_t* pv_done = p_full + 4;                // [tile]
   uint64_t* o_full = pv_done + 2;                // [tile]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;                 // [tile]  softmax -> MMA (kEarlyS): S_t is in registers, overwrite it
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,6 +271,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       mbar_init(&p_full[2 * t + 1], 4 * kCtas);
       mbar_init(&pv_done[t], 1);
       mbar_init(&o_full[t], 1);
+      mbar_init(&s_free[t], 4 * kCtas);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -390,9 +407,10 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
         if constexpr (kCtas == 2) umma_ts_pair(d, a, b, idesc, acc); else umma_ts(d, a, b, idesc, acc);
       };
-      // p_full collects remote arrives of the peer CTA's softmax warps: acquire at cluster scope
+      // p_full also collects remote arrives of the peer CTA's softmax warps (default .release.cta arrives: what they
+      // publish -- P in the peer's TMEM / shared memory -- is consumed by the peer's half of the pair MMA)
       auto wait_p = [&](uint64_t* bar, uint32_t par) {
-        if constexpr (kCtas == 2) mbar_wait_cluster(bar, par); else mbar_wait(bar, par);
+        mbar_wait(bar, par);
         tc_fence_after();
       };
 
@@ -438,6 +456,20 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
         __syncwarp();
       };
+      // kEarlyS: 64-key half `half` of P_t from its own panel (2 t + half); the very first MMA of a segment overwrites O
+      auto issue_pv_panel = [&](int t, int v_ring, int half, bool first_step) {
+        const uint64_t va = v_desc + (v_ring % kStages) * kStage16;
+        const uint64_t pa = p_desc + (2 * t + half) * (kHalfTile >> 4);
+        const uint32_t d = tmem_base + 256 + t * kHeadDim;
+        const uint32_t acc0 = (first_step && half == 0) ? 0u : 1u;
+        if (elect_one()) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            mma_ss(d, pa + ((k4 * 32) >> 4), va + (4 * half + k4) * (2048 >> 4), idesc_pv, k4 > 0 ? 1u : acc0);
+          }
+        }
+        __syncwarp();
+      };
       auto issue_pv = [&](int t, int v_ring, bool first_step, int kk0) {   // 4 K-steps = 64 keys from kk0
         const uint64_t va = v_desc + (v_ring % kStages) * kStage16;
         const uint32_t d = tmem_base + 256 + t * kHeadDim;
@@ -455,6 +487,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
 
       int ring = 0;     // K/V tiles consumed so far (all segments)
       int gstep = 0;    // softmax/MMA steps so far (all segments)
+      [[maybe_unused]] long long pf_p0 = 0, pf_p1 = 0, pf_kv = 0, pf_q = 0;
+      [[maybe_unused]] const long long pf_start = clock64();
       for (int si = 0; si < sch.n_seg; ++si) {
         const FmhaSeg sg = sch.seg(si);
         int batch, head, q_row0, k_len, ka, kb;
@@ -462,7 +496,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         const int n_steps = kb - ka;
         const int qb = si % kQBufs;
         const uint32_t qpar = (si / kQBufs) & 1;
-        mbar_wait(&q_full[2 * qb], qpar);
+        UVB_PROF(pf_q, mbar_wait(&q_full[2 * qb], qpar));
         tc_fence_after();
         if (n_steps == 0) {
           // nothing to attend to (k_lens clipped the range away): the epilogue treats O as zero
@@ -472,7 +506,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           continue;
         }
         // prologue: scores of the first step of both tiles
-        wait_full(ring);
+        UVB_PROF(pf_kv, wait_full(ring));
         issue_qk(2 * qb, 0, ring);
         commit(&s_full[0]);
         mbar_wait(&q_full[2 * qb + 1], qpar);
@@ -486,11 +520,35 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           const int v_ring = ring + 2 * step + 1;
           const int k_ring = v_ring + 1;          // K tile of the next step
           const bool more = step + 1 < n_steps;
-          wait_full(v_ring);
+          UVB_PROF(pf_kv, wait_full(v_ring));
+          if constexpr (kEarlyS) {
+            // S_t is free as soon as the softmax group holds it in registers (s_free), long before any of P_t exists:
+            // the next score tile is issued then, so Q K^T is off the softmax -> MMA -> softmax chain altogether and
+            // the (cross-CTA) signalling latencies hide under a whole softmax step.  Both halves of P come through
+            // shared memory.
+#pragma unroll
+            for (int t = 0; t < kQTiles; ++t) {
+              if (more) {
+                UVB_PROF(pf_p0, wait_p(&s_free[t], par));
+                if (t == 0) UVB_PROF(pf_kv, wait_full(k_ring));
+                issue_qk(2 * qb + t, t, k_ring);
+                commit(&s_full[t]);
+              }
+              UVB_PROF(pf_p0, wait_p(&p_full[2 * t + 0], par));
+              issue_pv_panel(t, v_ring, 0, step == 0);
+              UVB_PROF(pf_p1, wait_p(&p_full[2 * t + 1], par));
+              issue_pv_panel(t, v_ring, 1, step == 0);
+              commit(&pv_done[t]);
+              if (!more) commit(&o_full[t]);
+            }
+            commit(&kv_empty[v_ring % kStages]);
+            if (more) commit(&kv_empty[k_ring % kStages]);
+            continue;
+          }
 #pragma unroll
           for (int t = 0; t < kQTiles; ++t) {
             // split-P: the first 64 keys of P_t are signalled while the softmax still works on the rest
-            wait_p(&p_full[2 * t + 0], par);
+            UVB_PROF(pf_p0, wait_p(&p_full[2 * t + 0], par));
             issue_pv(t, v_ring, step == 0, 0);
             if constexpr (kPSmem) {
               // The first half of P has arrived, so all of S_t sits in the softmax registers, and the PV just
@@ -499,16 +557,16 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
               // memory, not through S_t).  Only the last 64 keys of PV stay on the softmax -> MMA -> softmax
               // dependency chain; QK^T leaves it.
               if (more) {
-                if (t == 0) wait_full(k_ring);
+                if (t == 0) UVB_PROF(pf_kv, wait_full(k_ring));
                 issue_qk(2 * qb + t, t, k_ring);
                 commit(&s_full[t]);
               }
-              wait_p(&p_full[2 * t + 1], par);
+              UVB_PROF(pf_p1, wait_p(&p_full[2 * t + 1], par));
               issue_pv_smem(t, v_ring);
               commit(&pv_done[t]);
               if (!more) commit(&o_full[t]);
             } else {
-              wait_p(&p_full[2 * t + 1], par);
+              UVB_PROF(pf_p1, wait_p(&p_full[2 * t + 1], par));
               issue_pv(t, v_ring, step == 0, 4);
               commit(&pv_done[t]);
               if (more) {
@@ -526,6 +584,17 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         ring += 2 * n_steps;
         gstep += n_steps;
       }
+#ifdef UVB_FMHA_PROFILE
+      if (p.prof != nullptr && lane == 0) {
+        unsigned long long* pr = p.prof + blockIdx.x * 16;
+        pr[6] = clock64() - pf_start;
+        pr[7] = pf_p0;
+        pr[8] = pf_p1;
+        pr[9] = pf_kv;
+        pr[10] = pf_q;
+        pr[11] = gstep;
+      }
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -538,9 +607,12 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     const uint32_t tO = tmem_base + lane_addr + 256 + t * kHeadDim;
     const float scale_log2 = p.scale_log2;
     const int ws_row = t * kBlockM + row;          // row inside the unit
-    // pair: p_full lives in the leader CTA
+    // pair: p_full / s_free live in the leader CTA
     const uint32_t p_full_cl = kCtas == 2 ? map_to_cta(&p_full[0], 0) : 0u;
+    const uint32_t s_free_cl = kCtas == 2 ? map_to_cta(&s_free[0], 0) : 0u;
     bool stored = false;
+    [[maybe_unused]] long long pf_s = 0, pf_pv = 0;
+    [[maybe_unused]] const long long pf_start = clock64();
     int pending_qb = -1;   // kQBufs == 2: query buffer whose O store was issued but not yet released
     int gstep = 0;
     // With two query buffers the release of a buffer (its O store must have finished READING the staging
@@ -573,7 +645,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       for (int step = 0; step < n_steps; ++step) {
         const uint32_t par = (gstep + step) & 1;
         const int key0 = (ka + step) * kBlockN;
-        mbar_wait(&s_full[t], par);
+        UVB_PROF(pf_s, mbar_wait(&s_full[t], par));
         tc_fence_after();
         uint32_t sr[kBlockN];
         tmem_ld_x32(tS, sr);
@@ -581,6 +653,19 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         tmem_ld_x32(tS + 64, sr + 64);
         tmem_ld_x32(tS + 96, sr + 96);
         tmem_wait_ld();
+        if constexpr (kEarlyS) {
+          // S_t is in registers: hand the TMEM tile back (the last step of a segment has no successor to wait for
+          // it, but arriving unconditionally keeps the barrier phase equal to the step count)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 2) {
+              mbar_arrive_remote(s_free_cl + t * 8);
+            } else {
+              mbar_arrive(&s_free[t]);
+            }
+          }
+        }
 
         if constexpr (kKeyMod) {
           if (p.key_logit_scale != nullptr) {
@@ -604,15 +689,18 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           }
         }
 
+        // four independent chains of three-input maxima (FMNMX3): 64 instructions for 128 scores
         float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
         float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
 #pragma unroll
-        for (int c = 4; c < kBlockN; c += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+        for (int c = 4; c + 8 <= kBlockN; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
         }
+        mx0 = fmax3(mx0, __uint_as_float(sr[kBlockN - 4]), __uint_as_float(sr[kBlockN - 3]));
+        mx1 = fmax3(mx1, __uint_as_float(sr[kBlockN - 2]), __uint_as_float(sr[kBlockN - 1]));
         const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
         if (step == 0) {
@@ -622,7 +710,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           if (__any_sync(0xffffffffu, need)) {
             // O_t may still be accumulating PV_t(step-1): wait for it.  PV_t(step) cannot be issued
             // before we arrive on p_full below, so pv_done[t] is at most one phase ahead of us.
-            mbar_wait(&pv_done[t], par ^ 1);
+            UVB_PROF(pf_pv, mbar_wait(&pv_done[t], par ^ 1));
             tc_fence_after();
             const float m_new = fmaxf(m, tile_max);
             const float f = ex2_approx((m - m_new) * scale_log2);
@@ -649,17 +737,18 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          if (kPSmem && h == 1) {
+          if (kEarlyS || (kPSmem && h == 1)) {
             // second half -> shared memory, row `row` of the K-major SWIZZLE_128B panel of this tile (the
             // PV of the previous step must have finished reading the panel: pv_done, long since complete).
             // (Handing the generic->async proxy fence and the arrive to a helper warp behind a named barrier
             // takes ~230 cycles per step off this warp but adds as much to the hand-off latency of the last
             // PV, which is on the dependency chain: measured slower.)
             uint32_t pk[32];
-            softmax_exp<32, kKeyMod>(sr + 64, scale_log2, neg_ms, sum_a, sum_b, pk,
-                                                 pvw == nullptr ? nullptr : pvw + 64);
-            if (gstep + step > 0) mbar_wait(&pv_done[t], par ^ 1);
-            uint8_t* prow = smem_p + t * kHalfTile + row * 128;
+            softmax_exp<32, kKeyMod, kPoly>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
+                                     pvw == nullptr ? nullptr : pvw + 64 * h);
+            // the previous step's PV must have finished reading the panel(s) of this tile
+            if (gstep + step > 0 && (!kEarlyS || h == 0)) UVB_PROF(pf_pv, mbar_wait(&pv_done[t], par ^ 1));
+            uint8_t* prow = smem_p + (kEarlyS ? 2 * t + h : t) * kHalfTile + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
@@ -668,7 +757,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             fence_proxy_async_smem();
           } else {
             uint32_t pk[32];
-            softmax_exp<32, kKeyMod>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
+            softmax_exp<32, kKeyMod, kPoly>(sr + 64 * h, scale_log2, neg_ms, sum_a, sum_b, pk,
                                                  pvw == nullptr ? nullptr : pvw + 64 * h);
             tmem_st_x32(tS + 32 * h, pk);
             tmem_wait_st();
@@ -677,7 +766,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           __syncwarp();
           if (lane == 0) {                                   // one barrier per 64-key half (split-P)
             if constexpr (kCtas == 2) {
-              mbar_arrive_cluster(p_full_cl + (2 * t + h) * 8);
+              mbar_arrive_remote(p_full_cl + (2 * t + h) * 8);
             } else {
               mbar_arrive(&p_full[2 * t + h]);
             }
@@ -871,6 +960,14 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
     }
     if constexpr (kQBufs == 2) release_pending();
     if (stored) tma_store_wait0();
+#ifdef UVB_FMHA_PROFILE
+    if (p.prof != nullptr && wq == 0 && lane == 0) {
+      unsigned long long* pr = p.prof + blockIdx.x * 16 + 3 * t;
+      pr[0] = clock64() - pf_start;
+      pr[1] = pf_s;
+      pr[2] = pf_pv;
+    }
+#endif
     if (p.timeline != nullptr && threadIdx.x == 0)
       p.timeline[blockIdx.x * 32 + 1 + min(sch.n_seg, 30)] = globaltimer_ns();
   }

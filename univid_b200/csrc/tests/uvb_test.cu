@@ -16,6 +16,10 @@
 
 #include "../../../include/univid_b200.h"
 
+#ifdef UVB_FMHA_PROFILE
+extern "C" void uvb_debug_fmha_profile(void* device_buffer);
+#endif
+
 #define CK(x)                                                                              \
   do {                                                                                     \
     cudaError_t e = (x);                                                                   \
@@ -243,6 +247,43 @@ static int run_fmha(int argc, char** argv) {
       printf(" | %7.1f\n", (tl[g * 32 + k - 1] - t0) * 1e-3);
     }
   }
+#ifdef UVB_FMHA_PROFILE
+  {
+    // wait-cycle counters of one warm launch (library built with -DUVB_FMHA_PROFILE)
+    unsigned long long* dpr;
+    const int nsm = 148;
+    CK(cudaMalloc(&dpr, nsm * 16 * 8));
+    launch();
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(dpr, 0, nsm * 16 * 8));
+    uvb_debug_fmha_profile(dpr);
+    launch();
+    CK(cudaDeviceSynchronize());
+    uvb_debug_fmha_profile(nullptr);
+    std::vector<unsigned long long> pr(nsm * 16);
+    CK(cudaMemcpy(pr.data(), dpr, nsm * 16 * 8, cudaMemcpyDeviceToHost));
+    static const char* names[12] = {"sm0_total", "sm0_wait_S", "sm0_wait_PV", "sm1_total", "sm1_wait_S", "sm1_wait_PV",
+                                    "mma_total", "mma_wait_P0", "mma_wait_P1", "mma_wait_KV", "mma_wait_Q", "steps"};
+    for (int par = 0; par < 2; ++par) {       // even CTAs (leaders of pairs) and odd CTAs separately
+      double sum[12] = {0};
+      int n = 0;
+      for (int g = par; g < nsm; g += 2) {
+        if (!pr[g * 16 + 0]) continue;
+        ++n;
+        for (int i = 0; i < 12; ++i) sum[i] += (double)pr[g * 16 + i];
+      }
+      if (!n) continue;
+      printf("PROF %s CTAs (%d):", par ? "odd " : "even", n);
+      const double steps = sum[11] > 0 ? sum[11] / n : 0;
+      for (int i = 0; i < 12; ++i) printf(" %s=%.0f", names[i], sum[i] / n);
+      if (steps > 0)
+        printf("\n     per step: sm0 %.0f (S %.0f, PV %.0f)  sm1 %.0f (S %.0f, PV %.0f)  mma %.0f (P0 %.0f P1 %.0f KV %.0f)",
+               sum[0] / n / steps, sum[1] / n / steps, sum[2] / n / steps, sum[3] / n / steps, sum[4] / n / steps,
+               sum[5] / n / steps, sum[6] / n / steps, sum[7] / n / steps, sum[8] / n / steps, sum[9] / n / steps);
+      printf("\n");
+    }
+  }
+#endif
   if (iters > 0) {
     // timing: inputs here exceed L2 only for the big shapes; flush L2 between iterations anyway
     char* flush;
@@ -576,7 +617,7 @@ static void apply_knobs() {
   const char* e = getenv("UVB_KNOBS");
   if (e == nullptr) return;
   static const char* names[UVB_KNOB_COUNT] = {"fmha_pair", "fmha_split", "gemm_ctas", "gemm_bn", "gemm_small",
-                                              "prologue_pair"};
+                                              "prologue_pair", "fmha_poly"};
   std::vector<char> buf(e, e + strlen(e) + 1);
   for (char* tok = strtok(buf.data(), ","); tok != nullptr; tok = strtok(nullptr, ",")) {
     char* eq = strchr(tok, '=');
