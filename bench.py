@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the Wan DiT attention hot path (BASELINE.json metric) -- prints ONE JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1.3B|14B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 14B|1.3B|5B]
     torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL; Ulysses head sharding)
 
-A *step* is the attention stack of one DiT forward (one denoise step) of the named config: for each of
-the model's layers, q/k WanRMSNorm + 3-D RoPE, self-attention over all video tokens, and the 512-key
-cross-attention.  `value` is attention TFLOP/s with the layer inputs (q/k/v projections) resident in
-HBM, measured over the kernels of this repo only; `e2e` is the same FLOPs divided by the time of the
-public module API (WanSelfAttention / WanCrossAttention .forward, q/k/v/o linears included) fed from
-pinned HOST memory with the result read back to the host every step.  `denoise_step_ms` additionally
-times the full WanModel.forward harness (all blocks with PyTorch linears / FFN) once.
+Headline workload at EVERY N: the north-star target config, Wan2.1-T2V-14B at 75 600 video tokens (40 heads shard
+over 1/2/4/8 GPUs), so the per-N values form a same-config strong-scaling curve.  The 1.3B / 32 760-token config
+(BASELINE configs[1..2]; N in {1, 2, 4}) and the text-weight sweep (configs[4]) ride along as sub-records of the same
+line (`configs`).
 
---impl reference times the reference's CPU path for the same metric: the oracle port of the reference
-modules (oracle/wan_attention_oracle.py; the reference itself is Python and cannot travel to the GPU
-box) on the host cores, on a bounded sample of the workload.
+A *step* is the attention stack of one DiT forward (one denoise step) of the named config: for each of the model's
+layers, q/k WanRMSNorm + 3-D RoPE, self-attention over all video tokens, and the 512-key cross-attention.  `value` is
+attention TFLOP/s with the layer inputs (q/k/v projections) resident in HBM, measured over the kernels of this repo
+only; `e2e` is the same FLOPs divided by the time of the public module API (WanSelfAttention / WanCrossAttention
+.forward, q/k/v/o linears included) fed from pinned HOST memory with the result read back to the host every step;
+`denoise_step` times the full WanModel.forward harness.  At N > 1 a full-size parity check of the sequence-parallel
+path (against the unsharded kernels and an fp32 re-evaluation of sampled rows) runs BEFORE the timed region and the
+process exits non-zero if it fails.
+
+--impl reference times the reference's own CPU implementation of the path: the unmodified reference modules staged
+under oracle/_ref by oracle/make_ref.py (kind "reference"; the oracle port if the staging is absent, kind "port") on
+all host cores, on a bounded sample of the workload.
 """
 import argparse
 import importlib
@@ -32,10 +38,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # BASELINE.json configs[1..3]: Wan2.1-T2V-1.3B, 81 frames 480x832 -> token grid (21, 30, 52)
+    # BASELINE.json configs[1..2]: Wan2.1-T2V-1.3B, 81 frames 480x832 -> token grid (21, 30, 52)
     "1.3B": dict(name="Wan2.1-T2V-1.3B denoise step, 81f 480x832", dim=1536, heads=12, layers=30, ffn=8960,
                  grid=(21, 30, 52), text_len=512),
-    # BASELINE.json configs[3]: Wan2.1-T2V-14B, 81 frames 720x1280 -> token grid (21, 45, 80)
+    # BASELINE.json configs[3] = the north-star target: Wan2.1-T2V-14B, 81 frames 720x1280 -> token grid (21, 45, 80)
     "14B": dict(name="Wan2.1-T2V-14B denoise step, 81f 720x1280", dim=5120, heads=40, layers=40, ffn=13824,
                 grid=(21, 45, 80), text_len=512),
     # the reference's own default model (not a BASELINE config; SURVEY.md sec. 8 geometry table, "ref native"):
@@ -44,12 +50,18 @@ CONFIGS = {
     "5B": dict(name="Wan2.2-TI2V-5B denoise step, 121f 704x1280", dim=3072, heads=24, layers=30, ffn=14336,
                grid=(31, 22, 40), text_len=512, in_dim=48, ti2v=True),
 }
+HEADLINE = "14B"
 
 
 def flops_per_layer(L, heads, text_len):
     f_self = 4.0 * L * L * heads * 128
     f_cross = 4.0 * L * text_len * heads * 128
     return f_self, f_cross
+
+
+def linear_flops_per_layer(L, dim, ffn, text_len):
+    """q/k/v/o of self-attention, q/o of cross-attention over L rows, k/v over the text rows, the two FFN GEMMs."""
+    return 2.0 * dim * dim * (6 * L + 2 * text_len) + 4.0 * L * dim * ffn
 
 
 def load_peaks():
@@ -88,11 +100,12 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                pw.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
@@ -101,25 +114,45 @@ class ClockSampler:
                     reasons.add(name)
         busy = sorted(sm)[len(sm) // 2:] if sm else []      # upper half = samples under load
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation (oracle port) on the host cores
+# reference arm: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------------
+def _host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can (rank 0 is the only rank working)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_rate(cfg, seconds_budget, steps, warmup):
-    """Times oracle.self_attention + oracle.cross_attention (bf16 autocast-equivalent, torch-SDPA route:
-    what the reference runs on CPU) for ONE layer on a bounded token sample.  Returns (tflops, ms_per_step,
-    sample description, threads)."""
+    """One layer of WanSelfAttention + WanCrossAttention (q/k/v/o linears included) under bf16 autocast on the CPU --
+    the reference's torch-SDPA route -- on a bounded token sample (whole latent frames) sized so that steps + warmup
+    runs fit the time budget.  Runs the UNMODIFIED reference modules when oracle/_ref (or /root/reference) is there
+    (`kind` "reference"), else the oracle port.  Returns (tflops, ms_per_step, sample, threads, kind)."""
+    from oracle import ref_loader
     from oracle import wan_attention_oracle as orc
+    threads = _host_threads()
     dim, heads, text_len = cfg["dim"], cfg["heads"], cfg["text_len"]
     f, h, w = cfg["grid"]
-    threads = torch.get_num_threads()
-    # probe at a small size to choose the largest frame count that fits the time budget
     g = torch.Generator().manual_seed(0)
     prm_s = orc.init_attention_params(dim, g)
     prm_c = orc.init_attention_params(dim, g)
     freqs = orc.make_freqs(128)
+    kind = "port"
+    sa = ca = None
+    if ref_loader.available():
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _, ref_model = ref_loader.load_modules()
+        sa, ca = ref_model.WanSelfAttention(dim, heads, eps=1e-6), ref_model.WanCrossAttention(dim, heads, eps=1e-6)
+        sa.load_state_dict(prm_s)
+        ca.load_state_dict(prm_c)
+        sa, ca = sa.eval(), ca.eval()
+        kind = "reference"
 
     def run(frames):
         L = frames * h * w
@@ -128,30 +161,34 @@ def cpu_reference_rate(cfg, seconds_budget, steps, warmup):
         gs, sl = torch.tensor([[frames, h, w]]), torch.tensor([L])
         t0 = time.perf_counter()
         with torch.no_grad():
-            orc.self_attention(x, prm_s, sl, gs, freqs, heads, 1e-6, bf16=True)
-            orc.cross_attention(x, ctx, prm_c, heads, None, 1e-6, bf16=True)
+            if sa is not None:
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    y = sa(x, sl, gs, freqs)
+                    ca(y, ctx, None)
+            else:
+                y = orc.self_attention(x, prm_s, sl, gs, freqs, heads, 1e-6, bf16=True)
+                orc.cross_attention(y, ctx, prm_c, heads, None, 1e-6, bf16=True)
         return time.perf_counter() - t0, L
 
     t_probe, l_probe = run(1)
+    t_probe2, _ = run(1)
+    t_probe = min(t_probe, t_probe2)
     per_step_budget = seconds_budget / max(steps + warmup, 1)
     frames = 1
     for cand in range(f, 0, -1):       # self-attention time grows ~quadratically with the token count
-        est = t_probe * (cand * h * w / l_probe) ** 2
-        if est <= per_step_budget:
+        if t_probe * (cand * h * w / l_probe) ** 2 <= per_step_budget:
             frames = cand
             break
     for _ in range(warmup):
         run(frames)
-    times = []
-    for _ in range(steps):
-        t, L = run(frames)
-        times.append(t)
+    times = [run(frames)[0] for _ in range(steps)]
     L = frames * h * w
     fs, fc = flops_per_layer(L, heads, text_len)
     sec = sum(times) / len(times)
     sample = (f"1 of {cfg['layers']} layers (WanSelfAttention + WanCrossAttention incl. q/k/v/o linears), "
-              f"{frames} of {f} latent frames = {L} of {f * h * w} video tokens, CPU bf16 torch-SDPA route")
-    return (fs + fc) / sec * 1e-12, sec * 1e3, sample, threads
+              f"{frames} of {f} latent frames = {L} of {f * h * w} video tokens, CPU bf16 torch-SDPA route, "
+              f"{'unmodified reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'}")
+    return (fs + fc) / sec * 1e-12, sec * 1e3, sample, threads, kind
 
 
 def run_reference_arm(args, cfg_key):
@@ -159,14 +196,14 @@ def run_reference_arm(args, cfg_key):
     if rank != 0:
         return
     cfg = CONFIGS[cfg_key]
-    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
-    tflops, ms, sample, threads = cpu_reference_rate(cfg, 150.0, steps, warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    tflops, ms, sample, threads, kind = cpu_reference_rate(cfg, 150.0, steps, warmup)
     line = {
         "impl": "reference", "metric": "dit_attention_tflops", "value": tflops, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": cfg["name"] + " -- attention stack", "sample": sample},
-        "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,24 +213,125 @@ def run_reference_arm(args, cfg_key):
 # ------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------
-def run_native_arm(args, cfg_key):
-    import torch.distributed as dist
+class Env:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_max_over_ranks(self, vals):
+        """vals: list of floats -> (min list, max list) over ranks."""
+        if self.world == 1:
+            return list(vals), list(vals)
+        lo = torch.tensor(vals, device=self.dev, dtype=torch.float64)
+        hi = lo.clone()
+        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN)
+        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX)
+        return lo.tolist(), hi.tolist()
+
+
+def _rows_reference(q, k, v, rows, k_len=None):
+    """fp32 softmax(q k^T / sqrt(d)) v for selected query rows; q/k/v [1, L, N, 128] bf16 on the GPU -> [R, N, D]."""
+    qf = q[0, rows].float().transpose(0, 1)
+    out = torch.empty(qf.shape, dtype=torch.float32, device=q.device)
+    for n in range(q.size(2)):                              # per head: bounded memory at 75 600 keys
+        s = torch.matmul(qf[n], k[0, :, n].float().t()) * 128 ** -0.5
+        if k_len is not None:
+            s[:, k_len:] = float("-inf")
+        out[n] = torch.matmul(torch.softmax(s, dim=-1), v[0, :, n].float())
+    return out.transpose(0, 1)
+
+
+def sp_parity_check(env, cfg, mdl, sp, _ext):
+    """Full-size parity of the sequence-parallel path, before anything is timed: one layer of
+    sp_attn_forward on this rank's token shard of a seeded x (identical on every rank) against
+      (i)  the same rows of the unsharded WanSelfAttention.forward on this GPU (same kernels, no exchange), and
+      (ii) an fp32 re-evaluation of sampled query rows against ALL keys (plain matmul + softmax, the oracle's
+           formula; tests/test_full_size_gpu.py) followed by the o projection in fp32 -- rows at both ends of the
+           rank's chunk, i.e. inside the 128-row output tiles that straddle two ranks' chunks.
+    Returns a dict; `ok` is the AND over all ranks."""
+    dim, heads = cfg["dim"], cfg["heads"]
+    f, h, w = cfg["grid"]
+    L = f * h * w
+    s = L // env.world
+    r = env.rank
+    bf = torch.bfloat16
+    torch.manual_seed(4321)
+    sa = mdl.WanSelfAttention(dim, heads).to(env.dev).eval()
+    for lin in (sa.q, sa.k, sa.v, sa.o):
+        torch.nn.init.xavier_uniform_(lin.weight)
+        torch.nn.init.normal_(lin.bias, std=0.02)
+    # logits ~ N(0, 2.5^2): a peaked softmax, so the outputs are not just the mean of v (which would make any
+    # absolute tolerance vacuous at 75 600 keys)
+    with torch.no_grad():
+        sa.norm_q.weight.fill_(2.5)
+    gen = torch.Generator(device=env.dev).manual_seed(99)          # identical on every rank
+    x = torch.randn(1, L, dim, device=env.dev, generator=gen).to(bf)
+    d = 128
+    table = torch.cat([mdl.rope_params(1024, d - 4 * (d // 6)), mdl.rope_params(1024, 2 * (d // 6)),
+                       mdl.rope_params(1024, 2 * (d // 6))], dim=1).to(env.dev)
+    grid_t, seq_lens = torch.tensor([[f, h, w]]), torch.tensor([L])
+    with torch.no_grad(), torch.autocast("cuda", dtype=bf):
+        mine = sp.sp_attn_forward(sa, x[:, r * s:(r + 1) * s].contiguous(), seq_lens, grid_t, table).float().clone()
+        full = sa(x, seq_lens, grid_t, table)[:, r * s:(r + 1) * s].float()
+        # (ii) fp32 rows: q/k after the fused prologue (bf16, what the attention kernel reads), v from the projection
+        q, k = sa._prologue(mdl._lin(sa.q, x), mdl._lin(sa.k, x), mdl._cos_sin_table(table, env.dev), grid_t)
+        v = mdl._lin(sa.v, x).view(1, L, heads, d)
+    local = sorted(set([0, 1, 63, 127, 128, s // 2, s - 129, s - 128, s - 65, s - 2, s - 1]))
+    local = [i for i in local if 0 <= i < s]
+    rows = torch.tensor([r * s + i for i in local], device=env.dev)
+    att = _rows_reference(q, k, v, rows)                                        # [R, N, D] fp32
+    want = att.flatten(1).to(bf).float() @ sa.o.weight.float().to(bf).float().t() + sa.o.bias.float().to(bf).float()
+    got = mine[0, local]
+    err_ref = (got - want).abs().max().item()
+    scale_ref = want.abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0).item()
+    err_unsharded = (mine - full).abs().max().item()
+    # a 128-row tile straddles two ranks' chunks whenever s is not a multiple of 128
+    ok_local = err_ref <= 2e-2 and cos >= 0.9999 and err_unsharded <= 8e-3 and bool(torch.isfinite(mine).all())
+    flag = torch.tensor([1.0 if ok_local else 0.0, -err_ref, -err_unsharded, cos, -err_ref / max(scale_ref, 1e-30)],
+                        device=env.dev, dtype=torch.float64)
+    if env.world > 1:
+        env.dist.all_reduce(flag, op=env.dist.ReduceOp.MIN)
+    del sa, x, q, k, v, full, mine
+    torch.cuda.empty_cache()
+    return {"ok": bool(flag[0].item() == 1.0), "max_abs_vs_fp32_rows": -flag[1].item(), "cos_vs_fp32_rows": flag[3].item(),
+            "max_abs_vs_unsharded_kernel": -flag[2].item(), "max_abs_over_output_max": -flag[4].item(),
+            "rows_per_rank": len(local),
+            "tokens_per_rank": s, "tile_straddles_ranks": s % 128 != 0, "tolerance": "max_abs <= 2e-2, cos >= 0.9999",
+            "what": "one layer of sp_attn_forward at the full benchmark size, every rank, worst over ranks"}
+
+
+def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=True, e2e=True):
+    """All measurements of one config on the current world.  Returns a dict (identical on every rank except for
+    rank-local diagnostics)."""
     from univid_b200 import _ext
     mdl = importlib.import_module("univid_b200.wan.modules.model")
     sp = importlib.import_module("univid_b200.wan.distributed.sequence_parallel")
     uly = importlib.import_module("univid_b200.wan.distributed.ulysses")
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dist, world, rank, dev, peaks = env.dist, env.world, env.rank, env.dev, env.peaks
 
     cfg = CONFIGS[cfg_key]
     dim, heads, layers, text_len = cfg["dim"], cfg["heads"], cfg["layers"], cfg["text_len"]
@@ -202,14 +340,22 @@ def run_native_arm(args, cfg_key):
     if heads % world != 0 or L % world != 0:
         raise SystemExit(f"{heads} heads / {L} tokens cannot be sharded over {world} ranks")
     s = L // world
-    peaks = load_peaks()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     bf = torch.bfloat16
+    res = {"config_key": cfg_key}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---------------- parity first (N > 1): nothing is timed on a path that is not proven on this box
+    ctx = None
+    if world > 1:
+        p2p = importlib.import_module("univid_b200.wan.distributed.p2p")
+        res["parity_check"] = sp_parity_check(env, cfg, mdl, sp, _ext)
+        if not res["parity_check"]["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "sequence-parallel parity check failed", "config": cfg_key,
+                                  "parity_check": res["parity_check"]}))
+            env.barrier()
+            sys.exit(3)
+        ctx = p2p.context(1, s, heads, dev)
 
     # ---------------- device-resident layer inputs (rotating sets, each far larger than the 126 MB L2)
     n_sets = 4
@@ -229,101 +375,112 @@ def run_native_arm(args, cfg_key):
     cs = mdl._cos_sin_table(table, dev)
     grid = [(f, h, w)]
     seq_lens = torch.tensor([L])
-    fmha_events, prol_events = [], []
-    ctx = None
-    if world > 1:
-        p2p = importlib.import_module("univid_b200.wan.distributed.p2p")
-        ctx = p2p.context(1, s, heads, dev)
+    marks = []              # [(name, event)] of the recorded steps, in stream order
 
     def kernel_step(record):
         """P + S + X of every layer through the C ABI; with world > 1 the Ulysses exchange around S."""
+        def mark(name):
+            if record:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
         for layer in range(layers):
             t = sets[layer % n_sets]
+            mark("begin")
             if world == 1:
-                if record:
-                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-                    ev[0].record()
                 q, k = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid)
-                if record:
-                    ev[1].record()
+                mark("prologue")
                 _ext.fmha_fwd(q, k, t["v"])
-                if record:
-                    ev[2].record()
-                    prol_events.append((ev[0], ev[1]))
-                    fmha_events.append((ev[1], ev[2]))
+                mark("self_attention")
             elif ctx is not None:
                 # fused exchange: producers store into the peers' buffers, attention stores o into the owners'
                 ctx.next_epoch()
                 _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid,
                                   tok_offset=rank * s, groups=world,
                                   peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
+                mark("prologue")
                 _ext.head_scatter(t["v"], world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
-                ctx.attend(None)
+                mark("head_scatter")
+                ctx.attend(None, mark=mark)          # marks: qkv_wait, self_attention, o_wait
             else:
                 q_send, k_send = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs,
                                                    grid_sizes=grid, tok_offset=rank * s, groups=world)
+                mark("prologue")
                 v_send = _ext.head_scatter(t["v"], world)
+                mark("head_scatter")
                 uly.attend_exchanged(q_send, k_send, v_send, seq_lens)
+                mark("nccl_exchange_and_attention")
             qc, _ = _ext.qk_norm_rope(t["qc"], None, wn, None, 1e-6, heads)
             _, kc = _ext.qk_norm_rope(None, t["kc"], None, wn, 1e-6, heads)
+            mark("cross_prologue")
             _ext.fmha_fwd(qc, kc, t["vc"])
+            mark("cross_attention")
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, record_last=False):
         for _ in range(warmup):
             fn(False)
-        barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
+        env.barrier()
+        sampler = ClockSampler(env.local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _ext.launch_count
         e0.record()
-        for _ in range(steps):
-            fn(True)
+        for i in range(steps):
+            fn(record_last and i == steps - 1)
         e1.record()
-        barrier()
+        env.barrier()
         clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            tms = torch.tensor([ms], device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
+        ms = env.max_over_ranks(e0.elapsed_time(e1) / steps)
         return ms, (_ext.launch_count - n0), clocks
 
     fs, fc = flops_per_layer(L, heads, text_len)
     flop_step = (fs + fc) * layers
     with torch.no_grad():
-        ms_kernel, launches, clocks = timed(kernel_step, args.steps, args.warmup, sample_clocks=True)
-    value = flop_step / (ms_kernel * 1e-3) * 1e-12
+        ms_kernel, launches, clocks = timed(kernel_step, steps, warmup, sample_clocks=True, record_last=True)
+    res.update(value=flop_step / (ms_kernel * 1e-3) * 1e-12, ms_per_step=ms_kernel, gpu_launches=launches, clocks=clocks,
+               attention_flop_per_step=flop_step)
 
-    roofline, roofline_prologue = None, None
+    # ---------------- per-kernel split of the last timed step (CUDA events on the launching stream) ----------
+    seg = {}
+    for (n0_, e0_), (n1_, e1_) in zip(marks[:-1], marks[1:]):
+        if n1_ == "begin":
+            continue
+        seg.setdefault(n1_, []).append(e0_.elapsed_time(e1_))
+    names = list(seg.keys())
+    avg = [sum(seg[n]) / len(seg[n]) for n in names]
+    lo, hi = env.min_max_over_ranks(avg)
+    split = {n: {"avg_ms_per_layer": a, "min_over_ranks": l_, "max_over_ranks": h_}
+             for n, a, l_, h_ in zip(names, avg, lo, hi)}
+    res["kernel_split"] = {"of": "last timed step, per layer, CUDA events", "segments": split,
+                           "sum_ms_per_step_this_rank": sum(avg) * layers}
+
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if world == 1 and fmha_events:
-        durs = [a.elapsed_time(b) for a, b in fmha_events]
-        avg = sum(durs) / len(durs)
-        achieved = fs / (avg * 1e-3) * 1e-12
-        traffic = None
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(cfg_key, {}).get("fmha_dram_bytes_per_launch")
-        roofline = {"kernel": "fmha_fwd_kernel (self-attention)", "bound": "tensor", "achieved": achieved,
-                    "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                    "frac_of_burst_peak": achieved / peaks["tflops_burst"], "peak_source": peaks["source"] +
-                    " sustained bf16 (kernel timed inside a long step)", "traffic": traffic,
-                    "avg_launch_ms": avg, "flop_per_launch": fs,
-                    "kernel_share_of_step": avg * layers / ms_kernel}
-        pavg = sum(a.elapsed_time(b) for a, b in prol_events) / len(prol_events)
+    traffic = json.load(open(tpath)).get(cfg_key, {}) if os.path.exists(tpath) else {}
+    heads_local = heads // world
+    if "self_attention" in seg:
+        a = sum(seg["self_attention"]) / len(seg["self_attention"])
+        fs_local = fs / world                                  # this rank's head shard
+        achieved = fs_local / (a * 1e-3) * 1e-12
+        res["roofline"] = {
+            "kernel": "fmha_fwd_kernel (self-attention" + (", CTA pairs" if _ext.lib().uvb_get_knob(0) == 1 else "") + ")",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+            "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+            "traffic": traffic.get("fmha_dram_bytes_per_launch") if world == 1 else None,
+            "avg_launch_ms": a, "flop_per_launch": fs_local, "heads_per_launch": heads_local,
+            "kernel_share_of_step": a * layers / ms_kernel}
+    if "prologue" in seg and world == 1:
+        pavg = sum(seg["prologue"]) / len(seg["prologue"])
         pbytes = 8.0 * L * dim
-        roofline_prologue = {"kernel": "qk_norm_rope_kernel (q/k RMSNorm + 3-D RoPE)", "bound": "hbm",
-                             "achieved": pbytes / (pavg * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"],
-                             "peak_source": peaks["source"] + " copy bandwidth", "avg_launch_ms": pavg,
-                             "bytes_per_launch": pbytes,
-                             "traffic": (json.load(open(tpath)).get(cfg_key, {}).get("prologue_dram_bytes_per_launch")
-                                         if os.path.exists(tpath) else None)}
+        res["roofline_prologue"] = {
+            "kernel": "qk_norm_rope_kernel (q/k RMSNorm + 3-D RoPE)", "bound": "hbm",
+            "achieved": pbytes / (pavg * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
+            "avg_launch_ms": pavg, "bytes_per_launch": pbytes, "traffic": traffic.get("prologue_dram_bytes_per_launch")}
 
     # ---------------- the block's largest GEMM (ffn[0] + tanh-GELU, SURVEY 8f rank 2), timed live -----
-    roofline_gemm = None
-    if world == 1:
+    if gemm_roofline and world == 1:
         ffn = cfg["ffn"]
         xg = sets[0]["q"].view(s, dim)
         wg = (torch.randn(ffn, dim, device=dev, generator=g) / dim ** 0.5).to(bf)
@@ -332,7 +489,7 @@ def run_native_arm(args, cfg_key):
         for _ in range(3):
             _ext.linear(xg, wg, bg, act=_ext.ACT_GELU_TANH, out=og)
         torch.cuda.synchronize()
-        n_g = 20
+        n_g = 20 if cfg_key != "14B" else 8
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(n_g):
@@ -341,58 +498,58 @@ def run_native_arm(args, cfg_key):
         torch.cuda.synchronize()
         gms = g0.elapsed_time(g1) / n_g
         gflop = 2.0 * s * ffn * dim
-        roofline_gemm = {"kernel": "gemm_bf16_kernel (ffn[0] + bias + tanh-GELU)", "bound": "tensor",
-                         "achieved": gflop / (gms * 1e-3) * 1e-12, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_sustained"],
-                         "frac_of_burst_peak": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_burst"],
-                         "peak_source": peaks["source"] + " sustained bf16 (20 launches back to back)",
-                         "avg_launch_ms": gms, "flop_per_launch": gflop, "shape_mnk": [s, ffn, dim],
-                         "traffic": (json.load(open(tpath)).get(cfg_key, {}).get("gemm_ffn0_dram_bytes_per_launch")
-                                     if os.path.exists(tpath) else None)}
+        res["roofline_gemm"] = {
+            "kernel": "gemm_bf16_kernel (ffn[0] + bias + tanh-GELU)", "bound": "tensor",
+            "achieved": gflop / (gms * 1e-3) * 1e-12, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_sustained"],
+            "frac_of_burst_peak": gflop / (gms * 1e-3) * 1e-12 / peaks["tflops_burst"],
+            "peak_source": peaks["source"] + f" sustained bf16 ({n_g} launches back to back)",
+            "avg_launch_ms": gms, "flop_per_launch": gflop, "shape_mnk": [s, ffn, dim],
+            "traffic": traffic.get("gemm_ffn0_dram_bytes_per_launch")}
         del wg, og
 
     # ---------------- e2e: public module API from pinned host memory ---------------------------------
-    torch.manual_seed(0)
-    sa = mdl.WanSelfAttention(dim, heads).to(dev).eval()
-    ca = mdl.WanCrossAttention(dim, heads).to(dev).eval()
-    for m in (sa, ca):
-        for lin in (m.q, m.k, m.v, m.o):
-            torch.nn.init.xavier_uniform_(lin.weight)
-            torch.nn.init.zeros_(lin.bias)
-    x_host = torch.randn(1, s, dim).to(bf).pin_memory()
-    ctx_host = torch.randn(1, text_len, dim).to(bf).pin_memory()
-    out_host = torch.empty(1, s, dim, dtype=bf).pin_memory()
-    grid_t = torch.tensor([[f, h, w]])
-    table_dev = table.to(dev)
+    if e2e:
+        torch.manual_seed(0)
+        sa = mdl.WanSelfAttention(dim, heads).to(dev).eval()
+        ca = mdl.WanCrossAttention(dim, heads).to(dev).eval()
+        for m in (sa, ca):
+            for lin in (m.q, m.k, m.v, m.o):
+                torch.nn.init.xavier_uniform_(lin.weight)
+                torch.nn.init.zeros_(lin.bias)
+        x_host = torch.randn(1, s, dim).to(bf).pin_memory()
+        ctx_host = torch.randn(1, text_len, dim).to(bf).pin_memory()
+        out_host = torch.empty(1, s, dim, dtype=bf).pin_memory()
+        grid_t = torch.tensor([[f, h, w]])
+        table_dev = table.to(dev)
 
-    def e2e_step(_record):
-        x = x_host.to(dev, non_blocking=True)
-        ctx = ctx_host.to(dev, non_blocking=True)
-        with torch.autocast("cuda", dtype=bf):
-            for _ in range(layers):
-                if world == 1:
-                    y = sa(x, seq_lens, grid_t, table_dev)
-                else:
-                    y = sp.sp_attn_forward(sa, x, seq_lens, grid_t, table_dev)
-                x = y + ca(y, ctx, None)
-        out_host.copy_(x, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def e2e_step(_record):
+            x = x_host.to(dev, non_blocking=True)
+            cx = ctx_host.to(dev, non_blocking=True)
+            with torch.autocast("cuda", dtype=bf):
+                for _ in range(layers):
+                    if world == 1:
+                        y = sa(x, seq_lens, grid_t, table_dev)
+                    else:
+                        y = sp.sp_attn_forward(sa, x, seq_lens, grid_t, table_dev)
+                    x = y + ca(y, cx, None)
+            out_host.copy_(x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    e2e_steps = max(1, min(args.steps, 5))
-    with torch.no_grad():
-        ms_e2e, _, _ = timed(e2e_step, e2e_steps, 1)
-    e2e = {"value": flop_step / (ms_e2e * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
-           "steps": e2e_steps,
-           "h2d_bytes_per_step": (x_host.numel() + ctx_host.numel()) * 2 * world,
-           "d2h_bytes_per_step": out_host.numel() * 2 * world,
-           "api": "WanSelfAttention.forward + WanCrossAttention.forward per layer (q/k/v/o linears included), "
-                  "x/context from pinned host memory, result copied back"}
+        with torch.no_grad():
+            ms_e2e, _, _ = timed(e2e_step, steps, warmup)
+        res["e2e"] = {"value": flop_step / (ms_e2e * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
+                      "steps": steps, "warmup": warmup,
+                      "h2d_bytes_per_step": (x_host.numel() + ctx_host.numel()) * 2 * world,
+                      "d2h_bytes_per_step": out_host.numel() * 2 * world,
+                      "api": "WanSelfAttention.forward + WanCrossAttention.forward per layer (q/k/v/o linears included), "
+                             "x/context from pinned host memory, result copied back"}
+        del sa, ca
 
     # ---------------- full denoise step through the WanModel harness ------------------------------------
     # N > 1: sp_attn_forward / sp_dit_forward are bound onto the instance exactly like the reference does
     # with use_sp=True (textimage2video.py:143-147): tokens sharded over the ranks, Ulysses around attention.
-    denoise_ms = None
-    if not args.skip_denoise:
+    if denoise:
         import types
         del sets
         torch.cuda.empty_cache()
@@ -413,72 +570,91 @@ def run_native_arm(args, cfg_key):
         tt = torch.full((1, L), 500.0, device=dev)
         if cfg.get("ti2v"):
             tt[0, :h * w] = 0.0
+        n_den = 2
         with torch.no_grad(), torch.autocast("cuda", dtype=bf):
             model(lat, tt, ctx_in, seq_len=L)
-            barrier()
+            env.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = _ext.launch_count
             e0.record()
-            for _ in range(2):
+            for _ in range(n_den):
                 model(lat, tt, ctx_in, seq_len=L)
             e1.record()
-            barrier()
-        denoise_ms = e0.elapsed_time(e1) / 2
-        if world > 1:
-            tms = torch.tensor([denoise_ms], device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            denoise_ms = float(tms.item())
+            env.barrier()
+        den_ms = env.max_over_ranks(e0.elapsed_time(e1) / n_den)
+        den_flop = flop_step + linear_flops_per_layer(L, dim, cfg["ffn"], text_len) * layers
+        den_tf = den_flop / (den_ms * 1e-3) * 1e-12
+        res["denoise_step"] = {
+            "ms": den_ms, "steps": n_den, "warmup": 1, "flop": den_flop, "tflops": den_tf,
+            "frac_of_sustained_peak": den_tf / (peaks["tflops_sustained"] * world),
+            "frac_of_burst_peak": den_tf / (peaks["tflops_burst"] * world),
+            "launches_per_step": (_ext.launch_count - n0) // n_den,
+            "what": "WanModel.forward, all blocks (attention + q/k/v/o + FFN GEMMs + glue) with per-token timesteps; "
+                    "flop = attention + block linears"}
         del model
+        torch.cuda.empty_cache()
+    res["sharding"] = ("none" if world == 1 else (
+        f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
+        if ctx is not None else f"Ulysses heads/{world} over NCCL all-to-all"))
+    res["geometry"] = {"video_tokens": L, "text_tokens": text_len, "dim": dim, "heads": heads, "layers": layers,
+                       "l2_policy": f"inputs larger than L2: 4 rotating layer-input sets of {3 * s * dim * 2 / 1e6:.0f} MB each"}
+    return res
 
-    if rank == 0:
+
+def run_native_arm(args, cfg_key):
+    env = Env(args)
+    cfg = CONFIGS[cfg_key]
+    main = measure(env, args, cfg_key, args.steps, args.warmup, denoise=not args.skip_denoise)
+    subs = {}
+    if not args.no_sub_records and cfg_key == HEADLINE:
+        # BASELINE configs[1..2]: the 1.3B model at 32 760 tokens (12 heads: 1, 2 or 4 GPUs)
+        if CONFIGS["1.3B"]["heads"] % env.world == 0:
+            sub = measure(env, args, "1.3B", min(args.steps, 10), 3, denoise=not args.skip_denoise, gemm_roofline=False)
+            subs["1.3B"] = {k: sub.get(k) for k in ("value", "ms_per_step", "e2e", "denoise_step", "roofline",
+                                                     "roofline_prologue", "kernel_split", "parity_check", "sharding",
+                                                     "geometry", "gpu_launches")}
+            subs["1.3B"]["unit"] = "TFLOP/s"
+            subs["1.3B"]["workload"] = CONFIGS["1.3B"]["name"] + " -- attention stack"
+        # BASELINE configs[4]: the text-weight sweep (query rows sharded, context replicated, no communication)
+        subs["tma_sweep"] = tma_sweep(env)
+    if env.rank == 0:
         cpu = None
-        if world == 1 and not args.skip_cpu:
-            tf, ms, sample, threads = cpu_reference_rate(cfg, 20.0, 2, 1)
-            cpu = {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample,
-                   "ms_per_sample": ms}
+        if env.world == 1 and not args.skip_cpu:
+            tf, ms, sample, threads, kind = cpu_reference_rate(cfg, 20.0, 2, 1)
+            cpu = {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample, "ms_per_sample": ms}
         line = {
-            "metric": "dit_attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel, "higher_is_better": True,
+            "metric": "dit_attention_tflops", "value": main["value"], "unit": "TFLOP/s", "n_gpus": env.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, "
-                       "512-key cross-attention) of all layers", "video_tokens": L, "text_tokens": text_len,
-                       "dim": dim, "heads": heads, "layers": layers,
-                       "sharding": "none" if world == 1 else (
-                           f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
-                           if ctx is not None else f"Ulysses heads/{world} over NCCL all-to-all"),
-                       "l2_policy": "inputs larger than L2: 4 rotating layer-input sets of "
-                                    f"{3 * s * dim * 2 / 1e6:.0f} MB each"},
-            "attention_flop_per_step": flop_step,
-            "denoise_step_ms": denoise_ms,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prologue": roofline_prologue,
-            "roofline_gemm": roofline_gemm,
-            "cpu_baseline": cpu,
+            "config": dict(workload=cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, "
+                           "512-key cross-attention) of all layers", sharding=main["sharding"], **main["geometry"]),
+            "attention_flop_per_step": main["attention_flop_per_step"],
+            "denoise_step_ms": (main.get("denoise_step") or {}).get("ms"),
+            "denoise_step": main.get("denoise_step"),
+            "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+            "parity_check": main.get("parity_check"),
+            "roofline": main.get("roofline"), "roofline_prologue": main.get("roofline_prologue"),
+            "roofline_gemm": main.get("roofline_gemm"), "kernel_split": main.get("kernel_split"),
+            "configs": subs, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------
 # BASELINE.json configs[4]: Temperature Modality Alignment cross-attention sweep
 # ------------------------------------------------------------------------------------------------------
-def run_tma_sweep(args):
+def tma_sweep(env):
     """512 text tokens x {32 760, 75 600} video tokens across the 50-step flow schedule (2 DiT calls per step
     with classifier-free guidance -> call index c = 0..99, weight w(c) from univid_b200.tma).  Per call: the
     text-weighted k-norm prologue on the 512 context rows + the fused cross-attention kernel (per-key
     post-softmax weight, value bias) -- `kernel` -- and the public WanCrossAttention.forward(text_weight=,
-    text_len=) with its q/k/v/o linears -- `module`.  Under torchrun every rank takes L/p query rows (no
+    text_len=) with its q/k/v/o linears -- `module`.  With several ranks every rank takes L/p query rows (no
     communication: the context is replicated)."""
-    import torch.distributed as dist
     from univid_b200 import _ext, tma
     mdl = importlib.import_module("univid_b200.wan.modules.model")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dist, world, dev = env.dist, env.world, env.dev
     bf = torch.bfloat16
     tcfg = tma.TextWeightConfig()
     calls = 2 * tcfg.total_sampling_steps
@@ -505,14 +681,12 @@ def run_tma_sweep(args):
             k_lin = (ca.k(ctx).float() - b_k).to(bf).contiguous()
             v_lin = (ca.v(ctx).float() - b_v).to(bf).view(1, text_len, heads, 128)
             wk = ca.norm_k.weight.float()
-            w_vecs = []
+            w_of = {}
             for wt in sorted(set(weights)):
                 v_ = torch.ones(text_len, dtype=torch.float32, device=dev)
                 v_[:tl] = wt
-                w_vecs.append((wt, v_))
-            w_of = dict(w_vecs)
+                w_of[wt] = v_
             out = torch.empty(1, s, heads, 128, dtype=bf, device=dev)
-
             v_f32 = v_lin.float()
 
             def kernel_call(c):
@@ -528,21 +702,14 @@ def run_tma_sweep(args):
             for name, fn in (("kernel", kernel_call), ("module", module_call)):
                 for c in range(3):
                     fn(c)
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
+                env.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for c in range(calls):
                     fn(c)
                 e1.record()
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / calls
-                if world > 1:
-                    t = torch.tensor([ms], device=dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    ms = float(t.item())
-                timing[name] = ms
+                timing[name] = env.max_over_ranks(e0.elapsed_time(e1) / calls)
         flop = 4.0 * L * text_len * heads * 128
         bytes_x = 4.0 * L * dim + 4.0 * text_len * dim
         res[key] = {"video_tokens": L, "heads": heads, "text_len_weighted": tl, "calls": calls,
@@ -552,19 +719,29 @@ def run_tma_sweep(args):
                     "module_tflops_attn_only": flop / (timing["module"] * 1e-3) * 1e-12}
         del ca, x, q, out
         torch.cuda.empty_cache()
-    if rank == 0:
-        peaks = load_peaks()
+    res["workload"] = ("Temperature Modality Alignment cross-attention sweep: 512 text tokens x {32760, 75600} video "
+                       "tokens, 50 flow steps x 2 CFG calls, cosine 1.3 -> 1.0")
+    res["weights_first_last"] = [weights[0], weights[-1]]
+    return res
+
+
+def run_tma_sweep(args):
+    env = Env(args)
+    res = tma_sweep(env)
+    if env.rank == 0:
+        peaks = env.peaks
         line = {"metric": "tma_cross_attention_sweep_tflops", "value": res["1.3B"]["kernel_tflops"], "unit": "TFLOP/s",
-                "n_gpus": world, "steps": calls, "warmup": 3, "ms_per_step": res["1.3B"]["kernel_ms_per_call"],
+                "n_gpus": env.world, "steps": res["1.3B"]["calls"], "warmup": 3,
+                "ms_per_step": res["1.3B"]["kernel_ms_per_call"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "Temperature Modality Alignment cross-attention sweep: 512 text tokens x "
-                                       "{32760, 75600} video tokens, 50 flow steps x 2 CFG calls, cosine 1.3 -> 1.0",
-                           "weights_first_last": [weights[0], weights[-1]], "transition_calls": int(50 * 0.4)},
-                "sweep": res, "peak_tflops_burst": peaks["tflops_burst"], "hbm_gbs": peaks["hbm_gbs"],
-                "gpu_launches": 2 * calls * 2}
+                "config": {"workload": res["workload"], "weights_first_last": res["weights_first_last"],
+                           "transition_calls": int(50 * 0.4)},
+                "sweep": {k: v for k, v in res.items() if k in ("1.3B", "14B")},
+                "peak_tflops_burst": peaks["tflops_burst"], "hbm_gbs": peaks["hbm_gbs"],
+                "gpu_launches": 2 * res["1.3B"]["calls"] * 2}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -573,16 +750,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default=None, choices=list(CONFIGS))
+    ap.add_argument("--config", default=None, choices=list(CONFIGS),
+                    help="headline config (default: 14B at every N -- the north-star target, same config at 1/2/4/8 GPUs)")
     ap.add_argument("--workload", default="attention", choices=["attention", "tma-sweep"],
-                    help="attention = the denoise-step attention stack (default, BASELINE configs[1..3]); "
-                         "tma-sweep = the text-weighted cross-attention sweep (configs[4])")
+                    help="attention = the denoise-step attention stack (default); tma-sweep = the text-weighted "
+                         "cross-attention sweep (BASELINE configs[4]) alone")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--skip-denoise", action="store_true", help="omit the full WanModel denoise-step timing")
+    ap.add_argument("--no-sub-records", action="store_true", help="omit the 1.3B and text-weight-sweep sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    # 12 heads shard over 2 / 4 GPUs (BASELINE configs[2]); 8 GPUs need the 40-head 14B model (configs[3])
-    cfg_key = args.config or ("14B" if args.gpus == 8 else "1.3B")
+    cfg_key = args.config or HEADLINE
     if args.impl == "reference":
         run_reference_arm(args, cfg_key)
     elif args.workload == "tma-sweep":

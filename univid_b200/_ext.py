@@ -20,7 +20,7 @@ EXPORTS = (
 )
 ABI_VERSION = 108
 KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
-         "fmha_poly": 6}
+         "fmha_poly": 6, "sp_wait_timeout_s": 7}
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes
@@ -120,6 +120,13 @@ def _ptr(t):
 
 
 def _stream(t):
+    """The current stream of t's device.  The C ABI launches on the CURRENT device (cudaGetDevice) and caches the SM
+    count / kernel attributes per current device, so the tensors must live there: refuse anything else loudly instead
+    of launching on the wrong GPU with a foreign stream handle."""
+    idx = t.device.index
+    if idx is not None and idx != torch.cuda.current_device():
+        raise RuntimeError(f"univid_b200: tensors are on cuda:{idx} but the current device is "
+                           f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device / use torch.cuda.device()")
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

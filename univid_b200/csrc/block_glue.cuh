@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(kGlueWarps * 32) block_glue_kernel(const __gri
   for (int i = 0; i < VPL; ++i) {
     const int c = (lane + kStride * i) * 8;
     float4 a0, a1;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "l"(xr + c));
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "l"(xr + c + 4));
+    // plain (coherent) streaming loads: x_out may alias x_in (in-place residual update), and .nc requires the
+    // memory to be read-only for the lifetime of the kernel
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "l"(xr + c) : "memory");
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "l"(xr + c + 4) : "memory");
     x[i][0] = a0.x; x[i][1] = a0.y; x[i][2] = a0.z; x[i][3] = a0.w;
     x[i][4] = a1.x; x[i][5] = a1.y; x[i][6] = a1.z; x[i][7] = a1.w;
   }

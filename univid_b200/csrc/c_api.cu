@@ -62,6 +62,7 @@ int g_knobs[UVB_KNOB_COUNT] = {
     /* UVB_KNOB_GEMM_SMALL    */ 1,   // single-wave 128x64 tiles for small problems
     /* UVB_KNOB_PROLOGUE_PAIR */ 1,   // token-pair prologue kernel when q and k are both given
     /* UVB_KNOB_FMHA_POLY     */ 0,   // CTA-pair attention kernel: 1 exp2 pair in every n on the FMA pipe (0, 2, 3, 4)
+    /* UVB_KNOB_SP_WAIT_TIMEOUT_S */ 600,   // seconds a rank waits for a peer's hand-off flag before trapping; 0 = for ever
 };
 
 int check_device() {
@@ -766,7 +767,10 @@ int uvb_sp_signal(void* const* flag_ptrs, int n, uint32_t value, void* stream) {
 
 int uvb_sp_wait(const void* flags, int n, uint32_t value, void* stream) {
   if (flags == nullptr || n <= 0 || n > 32) return fail(UVB_ERR_INVALID, "bad flag array");
-  uvb::sp_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(flags), n, value);
+  const int secs = g_knobs[UVB_KNOB_SP_WAIT_TIMEOUT_S];
+  const unsigned long long timeout_ns = secs <= 0 ? 0ull : static_cast<unsigned long long>(secs) * 1000000000ull;
+  uvb::sp_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(flags), n, value,
+                                                                       timeout_ns);
   UVB_CUDA(cudaGetLastError());
   return UVB_OK;
 }

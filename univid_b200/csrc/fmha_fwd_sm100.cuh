@@ -822,7 +822,9 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           if (ld_acquire_gpu(flag) == 0u) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(flag) == 0u) {
-              if (clock64() - t0 > 8000000000LL) __trap();
+              // other CTAs of this launch are co-resident, so a legitimate wait is microseconds; the bound only has
+              // to survive a preempted / time-sliced context (~1 min of SM clocks)
+              if (clock64() - t0 > 100000000000LL) __trap();
             }
           }
           const float* slot = p.ws + static_cast<size_t>(slot_of(gp)) * kWsSlotFloats;

@@ -448,15 +448,22 @@ __global__ void sp_signal_kernel(const __grid_constant__ SpSignalParams p) {
   }
 }
 
-// Spins until every flags[i] >= value (wrap-safe).  Bounded: after ~10 s without progress the kernel
-// traps (reported by the host as a launch failure) instead of hanging the GPU.
-__global__ void sp_wait_kernel(const uint32_t* flags, int n, uint32_t value) {
+// Spins until every flags[i] >= value (wrap-safe).  A rank may legitimately be seconds or minutes late (rank-0-only
+// VAE decode or save, offload_model reloads, lazy initialisation, a profiler pause), so the bound is generous and
+// configurable like a collective's watchdog: timeout_ns = 0 waits for ever; otherwise the kernel traps (reported by
+// the host as a launch failure) after that much wall time (%globaltimer) without the flag arriving.  Default 600 s
+// (UVB_KNOB_SP_WAIT_TIMEOUT_S), the default torch.distributed gives an NCCL collective.
+__global__ void sp_wait_kernel(const uint32_t* flags, int n, uint32_t value, unsigned long long timeout_ns) {
   if (threadIdx.x < n) {
     const uint32_t* f = flags + threadIdx.x;
-    const long long t0 = clock64();
-    while (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
-      if (clock64() - t0 > 20000000000LL) __trap();
-      __nanosleep(200);
+    if (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned backoff = 64;
+      while (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
+        if (timeout_ns != 0 && globaltimer_ns() - t0 > timeout_ns) __trap();
+        __nanosleep(backoff);
+        if (backoff < 2048) backoff <<= 1;      // late peers are polled every ~2 us, not hammered over NVLink
+      }
     }
   }
   __syncthreads();

@@ -21,6 +21,7 @@ and peers only store o of exchange e+1 after this rank's qkv-signal e+1, which i
 o_recv of exchange e (same stream).  `attend()` therefore returns a VIEW of o_recv that must be consumed on
 the current stream before the next exchange (the o projection does exactly that).
 """
+import atexit
 import ctypes
 import os
 import warnings
@@ -69,8 +70,17 @@ def exchange_layout(B, s, N, p, rank):
                 qkv_flag_bytes=4 * rank, o_flag_bytes=_O_FLAG_OFF + 4 * rank)
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not allocate / export / map the exchange buffers."""
+
+
 class UlyssesP2P:
     def __init__(self, B, s, N, device, group=None):
+        """Collective: every rank of `group` must call it.  Set-up runs in two phases (allocate + export, import) and
+        the ranks agree on success after each with an all_reduce(MIN), so that a failure on ONE rank (cudaMalloc,
+        cudaIpcGetMemHandle, cudaIpcOpenMemHandle for one peer) makes EVERY rank raise PeerExchangeUnavailable at the
+        same point, after executing the same collectives -- nobody is left waiting in a barrier -- and whatever was
+        allocated or mapped so far is released."""
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -83,23 +93,43 @@ class UlyssesP2P:
         elems = lay["elems"]
         self.off_q, self.off_k, self.off_v, self.off_o = lay["off_q"], lay["off_k"], lay["off_v"], lay["off_o"]
         self.nbytes = lay["nbytes"]
+        self.base, self.peer_base, self._imported, self._closed = 0, [], [], False
         lib = _ext.lib()
+
+        def agree(ok, what, err):
+            flag = torch.tensor([1.0 if ok else 0.0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if flag.item() == 0:
+                self.close()
+                raise PeerExchangeUnavailable(f"{what} failed on " + ("this rank: " + str(err) if not ok else "a peer rank"))
+
         with torch.cuda.device(device):
-            base = ctypes.c_void_p()
-            _ext._check(lib.uvb_sp_buffer_alloc(self.nbytes, ctypes.byref(base)))
-            self.base = int(base.value)
-            handle = ctypes.create_string_buffer(64)
-            _ext._check(lib.uvb_sp_ipc_export(self.base, handle))
+            # ---- phase 1: allocate + export
+            err, handle = None, ctypes.create_string_buffer(64)
+            try:
+                base = ctypes.c_void_p()
+                _ext._check(lib.uvb_sp_buffer_alloc(self.nbytes, ctypes.byref(base)))
+                self.base = int(base.value)
+                _ext._check(lib.uvb_sp_ipc_export(self.base, handle))
+            except RuntimeError as e:
+                err = e
+            agree(err is None, "exchange buffer allocation / IPC export", err)
             handles = [None] * p
             dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.peer_base = []
-            for j in range(p):
-                if j == self.rank:
-                    self.peer_base.append(self.base)
-                    continue
-                ptr = ctypes.c_void_p()
-                _ext._check(lib.uvb_sp_ipc_import(ctypes.create_string_buffer(handles[j], 64), ctypes.byref(ptr)))
-                self.peer_base.append(int(ptr.value))
+            # ---- phase 2: map every peer's buffer
+            err = None
+            try:
+                for j in range(p):
+                    if j == self.rank:
+                        self.peer_base.append(self.base)
+                        continue
+                    ptr = ctypes.c_void_p()
+                    _ext._check(lib.uvb_sp_ipc_import(ctypes.create_string_buffer(handles[j], 64), ctypes.byref(ptr)))
+                    self.peer_base.append(int(ptr.value))
+                    self._imported.append(int(ptr.value))
+            except RuntimeError as e:
+                err = e
+            agree(err is None, "IPC import of a peer's exchange buffer", err)
         n, r = self.n, self.rank
         slot = lay["slot_bytes"]                      # byte offset of slot (b = 0, i = rank) in a peer's q/k/v_recv
         self.q_peers = _ext.ptr_array([pb + self.off_q + slot for pb in self.peer_base])
@@ -133,14 +163,38 @@ class UlyssesP2P:
         _ext.sp_signal(self.o_flag_peers, self.world, self.epoch, stream)
         _ext.sp_wait(self.base + _O_FLAG_OFF, self.world, self.epoch, stream)
 
-    def attend(self, k_lens=None):
-        """q/k/v_recv (filled by the producers of this exchange) -> view of o_recv [B, s, N, 128]."""
+    def attend(self, k_lens=None, mark=None):
+        """q/k/v_recv (filled by the producers of this exchange) -> view of o_recv [B, s, N, 128].
+        mark: optional callable(name) invoked after each phase (bench.py records CUDA events with it)."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.qkv_ready(stream)
+        if mark is not None:
+            mark("qkv_signal_wait")
         _ext.fmha_fwd_sp(self.q_local, self.k_local, self.v_local, self.o_peers, self.world, self.rank * self.n,
                          self.N, k_lens=k_lens)
+        if mark is not None:
+            mark("self_attention")
         self.o_ready(stream)
+        if mark is not None:
+            mark("o_signal_wait")
         return self.o_local
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (idempotent).  The caller makes sure no kernel of ANY rank
+        still uses them (context teardown runs after a device synchronize + barrier when the group is still up)."""
+        if self._closed:
+            return
+        self._closed = True
+        lib = _ext.lib()
+        try:
+            with torch.cuda.device(self.device):
+                for ptr in self._imported:
+                    lib.uvb_sp_ipc_close(ptr)
+                if self.base:
+                    lib.uvb_sp_buffer_free(self.base)
+        except Exception:       # interpreter shutdown: the driver reclaims everything anyway
+            pass
+        self._imported, self.base = [], 0
 
 
 def context(B, s, N, device, group=None):
@@ -152,18 +206,31 @@ def context(B, s, N, device, group=None):
     if _DISABLED:
         return None
     key = (B, s, N, device.index, id(group))
-    ctx = _CONTEXTS.get(key)
-    if ctx is None:
-        ok = torch.ones(1, device=device)
+    if key not in _CONTEXTS:
         try:
-            ctx = UlyssesP2P(B, s, N, device, group)
-        except RuntimeError as e:          # IPC not permitted (container without shared IPC namespace, ...)
+            # raises PeerExchangeUnavailable on EVERY rank or on none (the constructor agrees per phase)
+            _CONTEXTS[key] = UlyssesP2P(B, s, N, device, group)
+        except PeerExchangeUnavailable as e:   # IPC not permitted (container without shared IPC namespace, ...)
             warnings.warn(f"univid_b200: NVLink peer exchange unavailable ({e}); using NCCL all-to-all")
-            ok.zero_()
-            ctx = None
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # all ranks take the same path
-        if ok.item() == 0:
-            ctx = None
+            _CONTEXTS[key] = None
             _DISABLED = True
-        _CONTEXTS[key] = ctx
-    return ctx
+    return _CONTEXTS[key]
+
+
+def close_all(synchronize=True):
+    """Release every exchange context of this process (buffers, IPC mappings).  Call it collectively before
+    dist.destroy_process_group(); it also runs at interpreter exit."""
+    ctxs = [c for c in _CONTEXTS.values() if c is not None]
+    if ctxs and synchronize:
+        try:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()
+        except Exception:
+            pass
+    for c in ctxs:
+        c.close()
+    _CONTEXTS.clear()
+
+
+atexit.register(close_all, False)

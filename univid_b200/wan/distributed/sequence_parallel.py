@@ -60,6 +60,13 @@ def sp_dit_forward(
     """WanModel.forward with the token dimension sharded over the ranks (sequence_parallel.py:64-144):
     embeddings are computed on every rank, each rank keeps its chunk of the tokens through the blocks
     and the head, and the outputs are all-gathered before unpatchify."""
+    # Re-align the ranks on the host once per DiT forward (one tiny NCCL collective, ~20 us against a forward of tens
+    # of milliseconds): whatever skew the ranks accumulated OUTSIDE the DiT (rank-0-only VAE decode or save, offload
+    # reloads, lazy initialisation) is absorbed here by a collective with torch.distributed's own watchdog, so the
+    # GPU-side flag waits of the fused exchange (uvb_sp_wait) only ever cover intra-forward skew.
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
     x, e, kwargs = self.embed(x, t, context, seq_len, y)
     world, rank = get_world_size(), get_rank()
     x = torch.chunk(x, world, dim=1)[rank]

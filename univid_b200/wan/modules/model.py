@@ -48,9 +48,11 @@ _COS_SIN_CACHE = {}
 
 
 def _cos_sin_table(freqs, device):
-    """fp32 [1024, 64, 2] (cos, sin) device table for the prologue kernel, cached per freqs tensor."""
-    key = (freqs.data_ptr(), tuple(freqs.shape), str(device))
-    tab = _COS_SIN_CACHE.get(key)
+    """fp32 [1024, 64, 2] (cos, sin) device table for the prologue kernel, cached per freqs tensor.  The key holds a
+    weak reference to the tensor (checked on every hit), so an address recycled for another table never aliases."""
+    key = (id(freqs), freqs.data_ptr(), tuple(freqs.shape), str(device))
+    hit = _COS_SIN_CACHE.get(key)
+    tab = hit[1] if hit is not None and hit[0]() is freqs and hit[2] == _version_of(freqs) else None
     if tab is None:
         if freqs.dim() != 2 or freqs.shape[1] != 64 or not freqs.is_complex():
             raise NotImplementedError('the RoPE kernel expects the [M, 64] complex table of head_dim 128')
@@ -60,7 +62,7 @@ def _cos_sin_table(freqs, device):
         tab = torch.stack([f.real[:1024], f.imag[:1024]], dim=-1).to(device=device, dtype=torch.float32).contiguous()
         if len(_COS_SIN_CACHE) > 16:
             _COS_SIN_CACHE.clear()
-        _COS_SIN_CACHE[key] = tab
+        _COS_SIN_CACHE[key] = (weakref.ref(freqs), tab, _version_of(freqs))
     return tab
 
 
@@ -136,7 +138,7 @@ def _proj_for_kernel(t):
 # modules (A/B against cuBLAS).
 # ----------------------------------------------------------------------------------------------------------
 _USE_GEMM = os.environ.get('UVB_LINEAR', '1') != '0'
-_LINEAR_CACHE = {}
+_LINEAR_ATTR = '_uvb_linear_operands'
 
 
 def _version_of(t):
@@ -147,23 +149,44 @@ def _version_of(t):
 
 
 def _linear_operands(mod):
-    """(weight bf16 [N, K], bias fp32 [N] holding bf16-rounded values | None) of an nn.Linear, cached until the
-    parameters change: autocast casts weight AND bias to bf16 on every call (the reference pays that cast per
-    autocast region); here the copy is made once per parameter version."""
+    """(weight bf16 [N, K], bias fp32 [N] holding bf16-rounded values | None) of an nn.Linear, cached ON THE MODULE
+    until the parameters change: autocast casts weight AND bias to bf16 on every call (the reference pays that cast
+    per autocast region); here the copy is made once per parameter version.  A bf16 parameter is used as it is (no
+    copy).  Invalidation: parameter identity, `_version` (optimizer steps, load_state_dict, copy_), storage address
+    and device (`.to()`, `.cpu()`); the drop-in modules also drop the copies in `_apply` (so `model.cpu()` releases
+    them at once) and when the module is garbage-collected.  NOT detected: in-place edits through `.data`
+    (`w.data += delta`, PEFT merge_and_unload) of an fp32 parameter -- call clear_linear_cache(model) after those."""
     w, b = mod.weight, mod.bias
-    key = id(w)
-    ver = (_version_of(w), w.data_ptr(), None if b is None else (_version_of(b), b.data_ptr()))
-    hit = _LINEAR_CACHE.get(key)
-    if hit is not None and hit[0]() is w and hit[1] == ver:
-        return hit[2], hit[3]
+    ver = (id(w), _version_of(w), w.data_ptr(), w.device, None if b is None else (id(b), _version_of(b), b.data_ptr()))
+    hit = mod.__dict__.get(_LINEAR_ATTR)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
     with torch.no_grad():
         wb = w.detach() if w.dtype == torch.bfloat16 else w.detach().to(torch.bfloat16)
         bb = None if b is None else b.detach().to(torch.bfloat16).float()
-    if len(_LINEAR_CACHE) > 4096:
-        for k in [k for k, v in _LINEAR_CACHE.items() if v[0]() is None]:
-            del _LINEAR_CACHE[k]
-    _LINEAR_CACHE[key] = (weakref.ref(w), ver, wb, bb)
+    mod.__dict__[_LINEAR_ATTR] = (ver, wb, bb)
     return wb, bb
+
+
+def clear_linear_cache(module=None):
+    """Drop the cached bf16 GEMM operands of every nn.Linear under `module` (required after editing weights through
+    `.data`, which no version counter sees).  Returns the number of entries dropped."""
+    if module is None:
+        raise TypeError('clear_linear_cache(module): pass the model (or sub-module) whose weights were edited')
+    n = 0
+    for m in module.modules():
+        if m.__dict__.pop(_LINEAR_ATTR, None) is not None:
+            n += 1
+    return n
+
+
+class _DropOperandsOnApply:
+    """Mixin: `.to()` / `.cpu()` / `.cuda()` / `.half()` go through nn.Module._apply -- drop the cached bf16 operand
+    copies first, so moving a model off the GPU (the reference's offload_model=True) frees them immediately."""
+
+    def _apply(self, fn, *args, **kwargs):
+        clear_linear_cache(self)
+        return super()._apply(fn, *args, **kwargs)
 
 
 def _gemm_ok(mod, x):
@@ -198,7 +221,7 @@ def _ffn_forward(ffn, h):
     return ffn(h)
 
 
-class WanSelfAttention(nn.Module):
+class WanSelfAttention(_DropOperandsOnApply, nn.Module):
 
     def __init__(self,
                  dim,
@@ -313,7 +336,7 @@ class WanCrossAttention(WanSelfAttention):
         return self._out_proj(x)
 
 
-class WanAttentionBlock(nn.Module):
+class WanAttentionBlock(_DropOperandsOnApply, nn.Module):
     """DiT block: adaLN-modulated self-attention, cross-attention, FFN (model.py:183-259)."""
 
     def __init__(self,
