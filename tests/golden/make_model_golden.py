@@ -19,7 +19,10 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "wan_model_golden.pt")
 KW = dict(model_type="t2v", dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, freq_dim=32, in_dim=4,
           out_dim=4, text_len=24, cross_attn_norm=True, eps=1e-6)
-SEQ_LEN = 80          # 3*4*6 = 72 and 2*4*4 = 32 real tokens, padded to 80
+SEQ_LEN = 72          # 3*4*6 tokens per sample, NO padding: the reference's CPU (torch-SDPA) route ignores k_lens
+                      # (attention.py:165-168) while its GPU (flash) route masks padded keys (:72-80); without padding
+                      # the two coincide, so this golden pins the semantics the product runs on a GPU
+PADDED_SEQ_LEN = 80   # padded variant (second sample 32 real tokens): checked against oracle.dit_forward(route="flash")
 
 
 def seeded_state(model, seed=11):
@@ -43,17 +46,19 @@ def seeded_state(model, seed=11):
     return out
 
 
-def model_case(seed=5):
+def model_case(seed=5, padded=False):
     g = torch.Generator().manual_seed(seed)
-    lat = [torch.randn(4, 3, 8, 12, generator=g), torch.randn(4, 2, 8, 8, generator=g)]
+    second = (4, 2, 8, 8) if padded else (4, 3, 8, 12)
+    lat = [torch.randn(4, 3, 8, 12, generator=g), torch.randn(*second, generator=g)]
     ctx = [torch.randn(20, 64, generator=g), torch.randn(9, 64, generator=g)]
+    seq_len = PADDED_SEQ_LEN if padded else SEQ_LEN
     # scalar-per-sample form: the reference's `t.expand(t.size(0), seq_len)` (model.py:461) only accepts B == 1,
     # so that case runs the first sample alone
     t_scalar = torch.tensor([500.0])
-    t_token = torch.full((2, SEQ_LEN), 700.0)
+    t_token = torch.full((2, seq_len), 700.0)
     t_token[0, :24] = 0.0          # first latent frame given (its tokens carry timestep 0)
     t_token[1, :16] = 0.0
-    return dict(lat=lat, ctx=ctx, t_scalar=t_scalar, t_token=t_token)
+    return dict(lat=lat, ctx=ctx, t_scalar=t_scalar, t_token=t_token, seq_len=seq_len)
 
 
 def checksums(case):
@@ -80,7 +85,7 @@ def run_reference_fp32(model_mod, att_mod, case, form):
     try:
         with torch.no_grad():
             lat, t, ctx = inputs_for(case, form)
-            return [u.clone() for u in m(lat, t, ctx, SEQ_LEN)]
+            return [u.clone() for u in m(lat, t, ctx, case["seq_len"])]
     finally:
         model_mod.flash_attention = orig
 

@@ -35,7 +35,7 @@ def test_golden_inputs_have_not_drifted(gold):
 def test_oracle_dit_forward_matches_reference_golden(gold, form):
     case, prm, kw = mg.model_case(), _state(), mg.KW
     lat, t, ctx = mg.inputs_for(case, form)
-    got = orc.dit_forward(lat, t, ctx, prm, mg.SEQ_LEN, kw["num_heads"], kw["num_layers"], kw["dim"], kw["freq_dim"],
+    got = orc.dit_forward(lat, t, ctx, prm, case["seq_len"], kw["num_heads"], kw["num_layers"], kw["dim"], kw["freq_dim"],
                           kw["text_len"], kw["out_dim"], eps=kw["eps"], bf16=False)
     want = gold[f"{form}_fp32"]
     assert len(got) == len(want)

@@ -441,6 +441,26 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
   const dim3 block(uvb::kNormRopeWarps * 32);
   // q and k together (self-attention): one warp group per token, both rows in flight (UVB_KNOB_PROLOGUE_PAIR = 0
   // keeps the one-row-per-group kernel)
+  // Self-attention form at the product's widths: the streaming kernel (persistent CTAs, bulk-copy ring)
+  if (g_knobs[UVB_KNOB_PROLOGUE_PAIR] == 2 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
+      p.row_scale == nullptr && sizeof(InT) == 2 && (dim == 1536 || dim == 3072 || dim == 5120)) {
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != UVB_OK) return rc;
+    auto launch = [&](auto kern, int dyn_bytes, int rows_per_stage) -> int {
+      UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes));
+      const long long chunks = (static_cast<long long>(p.B) * p.L + rows_per_stage - 1) / rows_per_stage;
+      const unsigned grid = static_cast<unsigned>(chunks < sms ? chunks : sms);
+      kern<<<grid, uvb::kStreamThreads, dyn_bytes, stream>>>(p);
+      UVB_CUDA(cudaGetLastError());
+      return UVB_OK;
+    };
+    switch (dim) {
+      case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers>, uvb::StreamSmem<6, 1>::kDynBytes, 8);
+      case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers>, uvb::StreamSmem<6, 2>::kDynBytes, 4);
+      default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers>, uvb::StreamSmem<5, 4>::kDynBytes, 2);
+    }
+  }
   const bool pair = g_knobs[UVB_KNOB_PROLOGUE_PAIR] != 0 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
                     p.row_scale == nullptr && sizeof(InT) == 2;
   if (pair) {

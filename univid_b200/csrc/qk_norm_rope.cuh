@@ -402,6 +402,233 @@ qk_norm_rope_pair_kernel(const __grid_constant__ NormRopeParams p) {
                                       1 + group);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Streaming form of the self-attention prologue (bf16 q AND k, no affine pre-map): persistent CTAs, one per SM.
+// Round-1 profile of the token-pair kernel above: 110 registers -> 2 CTAs per SM, 23 % warps active, DRAM busy
+// 55 %, ~600 warp instructions per row: every CTA alternates between a load phase (nothing to compute) and a
+// compute phase (nothing in flight), and under the power-capped clocks of a denoise step the instruction count
+// itself is a co-limiter.  Here the two concerns are decoupled:
+//   warp 8       producer: one elected lane streams the rows through a ring of shared-memory stages with 1-D bulk
+//                copies (cp.async.bulk, complete_tx on an mbarrier) -- a stage holds the q rows and the k rows of
+//                R = 8 / WPR consecutive tokens, which are contiguous in [B, L, dim], i.e. TWO copies per stage;
+//                ~150-200 KB per SM are in flight at any time regardless of what the compute warps do;
+//   warps 0-7    consumers: WPR warps per token; the row is read from shared memory and unpacked ONCE (registers are
+//                plentiful at one CTA per SM), the norm weights sit in shared memory, the token's (cos, sin) pairs are
+//                fetched once for q and k.
+// The arithmetic (order of operations, rounding points) is that of norm_rope_row: results are bit-identical.
+// ----------------------------------------------------------------------------------------------
+constexpr int kStreamConsumerWarps = 8;
+constexpr int kStreamThreads = (kStreamConsumerWarps + 1) * 32;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictFirst)
+      : "memory");
+}
+
+template <int VPL, int WPR>
+struct StreamSmem {
+  static constexpr int kDim = 256 * VPL * WPR;
+  static constexpr int kRowBytes = kDim * 2;
+  static constexpr int kRows = kStreamConsumerWarps / WPR;          // tokens per stage
+  static constexpr int kStageBytes = 2 * kRows * kRowBytes;         // q rows | k rows
+  static constexpr int kWeightBytes = 2 * kDim * 4;                 // wq | wk, fp32
+  static constexpr int kFixed = kWeightBytes + 1024;                // + barriers, reduction scratch, alignment slack
+  static constexpr int kStagesMax = (232448 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesMax < 6 ? kStagesMax : 6;
+  static_assert(kStages >= 2, "at least two stages");
+  static constexpr int kWOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kWOff + kWeightBytes;              // full[kStages], empty[kStages], red[2][8]
+  static constexpr int kDynBytes = kBarOff + 2 * kStages * 8 + 2 * kStreamConsumerWarps * 4 + 128;
+};
+
+// one row (already in shared memory) -> normalised, rotated, bf16, stored
+template <int VPL, int WPR, bool kPeers>
+__device__ __forceinline__ void stream_row(const uint8_t* __restrict__ srow, const float* __restrict__ w_s,
+                                           bool normed, __nv_bfloat16* __restrict__ out_row,
+                                           __nv_bfloat16* const* peers, long long out_off, int hpg, long long out_sg,
+                                           float eps, bool rotate, const float (&cs)[8], int lane, float* red,
+                                           int bar_id) {
+  constexpr int kStride = 32 * WPR;
+  constexpr int kDim = 256 * VPL * WPR;
+  float x[VPL][8];
+  float2 ss2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(srow + (lane + kStride * i) * 16);
+    const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      x[i][2 * e] = __uint_as_float(wd[e] << 16);
+      x[i][2 * e + 1] = __uint_as_float(wd[e] & 0xffff0000u);
+      const float2 xx = make_float2(x[i][2 * e], x[i][2 * e + 1]);
+      ss2 = ffma2(xx, xx, ss2);
+    }
+  }
+  float ss = warp_sum(ss2.x + ss2.y);
+  if constexpr (WPR > 1) {
+    if ((lane & 31) == 0) red[lane >> 5] = ss;
+    named_bar_sync(bar_id, kStride);
+    ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) ss += red[i];
+  }
+  const float rinv = normed ? rsqrtf(ss / static_cast<float>(kDim) + eps) : 1.0f;
+  const bool flat = hpg * 128 == kDim && !kPeers;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + kStride * i;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = x[i][e];
+    if (normed) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + vec * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + vec * 8 + 4);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float2 r2 = make_float2(rinv, rinv);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        float2 t = fmul2(make_float2(y[e], y[e + 1]), r2);
+        RowVec<__nv_bfloat16>::round_in2(t.x, t.y);
+        t = fmul2(t, make_float2(ww[e], ww[e + 1]));
+        y[e] = t.x;
+        y[e + 1] = t.y;
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      float a = y[2 * pr], b = y[2 * pr + 1];
+      if (rotate) {
+        const float c = cs[2 * pr], sn = cs[2 * pr + 1];
+        const float ra = a * c - b * sn;
+        const float rb = fmaf(a, sn, b * c);
+        a = ra;
+        b = rb;
+      }
+      o[pr] = pack_bf16x2(a, b);
+    }
+    __nv_bfloat16* dst;
+    if (flat) {
+      dst = out_row + vec * 8;
+    } else {
+      const int n = vec >> 4;
+      const int d0 = (vec & 15) * 8;
+      if constexpr (kPeers) {
+        dst = peers[n / hpg] + out_off + (n % hpg) * 128 + d0;
+      } else {
+        dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+      }
+    }
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o[0]),
+                 "r"(o[1]), "r"(o[2]), "r"(o[3])
+                 : "memory");
+  }
+}
+
+template <int VPL, int WPR, bool kPeers>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
+  using SM = StreamSmem<VPL, WPR>;
+  constexpr int kStages = SM::kStages;
+  constexpr int kRows = SM::kRows;
+  extern __shared__ uint8_t stream_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stream_smem_raw) + 127) &
+                                             ~static_cast<uintptr_t>(127));
+  float* w_s = reinterpret_cast<float*>(smem + SM::kWOff);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+  uint64_t* empty = full + kStages;
+  float* red = reinterpret_cast<float*>(empty + kStages);      // [2][8]
+  const int warp = threadIdx.x >> 5;
+  const long long rows = static_cast<long long>(p.B) * p.L;
+  const long long n_chunks = (rows + kRows - 1) / kRows;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kStreamConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  // norm weights -> shared memory (nullptr = qk_norm disabled: never read)
+  for (int i = threadIdx.x; i < SM::kDim; i += kStreamThreads) {
+    w_s[i] = p.wq != nullptr ? __ldg(p.wq + i) : 1.0f;
+    w_s[SM::kDim + i] = p.wk != nullptr ? __ldg(p.wk + i) : 1.0f;
+  }
+  __syncthreads();
+
+  if (warp == kStreamConsumerWarps) {
+    // ------------------------------------------ producer ------------------------------------------
+    const __nv_bfloat16* qg = static_cast<const __nv_bfloat16*>(p.q_in);
+    const __nv_bfloat16* kg = static_cast<const __nv_bfloat16*>(p.k_in);
+    int it = 0;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+      const int slot = it % kStages;
+      mbar_wait(&empty[slot], ((it / kStages) & 1) ^ 1);
+      if (elect_one()) {
+        const long long r0 = c * kRows;
+        const long long nr = rows - r0 < kRows ? rows - r0 : kRows;
+        const uint32_t bytes = static_cast<uint32_t>(nr) * SM::kRowBytes;
+        uint8_t* dst = smem + slot * SM::kStageBytes;
+        mbar_arrive_expect_tx(&full[slot], 2 * bytes);
+        bulk_load_1d(dst, qg + r0 * SM::kDim, bytes, &full[slot]);
+        bulk_load_1d(dst + kRows * SM::kRowBytes, kg + r0 * SM::kDim, bytes, &full[slot]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------ consumers -----------------------------------------
+    const int group = warp / WPR;                              // token inside the stage
+    const int lane = threadIdx.x - group * (32 * WPR);
+    const bool normed_q = p.wq != nullptr, normed_k = p.wk != nullptr;
+    int it = 0;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+      const int slot = it % kStages;
+      const long long row = c * kRows + group;
+      mbar_wait(&full[slot], (it / kStages) & 1);
+      if (row < rows) {
+        const int b = p.B == 1 ? 0 : static_cast<int>(row / p.L);
+        const int l = static_cast<int>(row - static_cast<long long>(b) * p.L);
+        float cs[8];
+        bool rotate = false;
+        if (p.cos_sin != nullptr) {
+          const int gb = b < kMaxBatchGrid ? b : kMaxBatchGrid - 1;
+          const int gh = p.grid[gb][1], gw = p.grid[gb][2];
+          const int tok = p.tok_offset + l;
+          rotate = tok < p.grid[gb][0] * gh * gw;
+          if (rotate) {
+            const int pf = tok / (gh * gw), ph = (tok / gw) % gh, pw = tok % gw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int jj = 4 * (lane & 15) + i;
+              const int pos = jj < 22 ? pf : (jj < 43 ? ph : pw);
+              const float2 v = __ldg(p.cos_sin + pos * 64 + jj);
+              cs[2 * i] = v.x;
+              cs[2 * i + 1] = v.y;
+            }
+          }
+        }
+        if (!rotate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+        }
+        const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
+        const uint8_t* sq = smem + slot * SM::kStageBytes + group * SM::kRowBytes;
+        const uint8_t* sk = sq + kRows * SM::kRowBytes;
+        stream_row<VPL, WPR, kPeers>(sq, w_s, normed_q, p.q_out + out_off, p.q_peer, out_off, p.hpg, p.out_sg, p.eps,
+                                     rotate, cs, lane, red + group * WPR, 1 + group);
+        stream_row<VPL, WPR, kPeers>(sk, w_s + SM::kDim, normed_k, p.k_out + out_off, p.k_peer, out_off, p.hpg,
+                                     p.out_sg, p.eps, rotate, cs, lane, red + kStreamConsumerWarps + group * WPR,
+                                     1 + group);
+      }
+      // both rows of this warp's token have been read out of the stage
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
+    }
+  }
+}
+
 // Head-group scatter of an un-normalised tensor (v) into the Ulysses send layout; pure copy.
 struct HeadScatterParams {
   const __nv_bfloat16* in;   // [B, L, N, 128]
