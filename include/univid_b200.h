@@ -49,7 +49,8 @@ enum uvb_knob {
   UVB_KNOB_GEMM_CTAS = 2,     /* 2: CTA-pair GEMM tiles (default); 1: single-CTA tiles */
   UVB_KNOB_GEMM_BN = 3,       /* 0: tile width chosen per problem (default); 192 | 256: pinned */
   UVB_KNOB_GEMM_SMALL = 4,    /* 1: one-wave 128x64 tiles for small problems (default); 0: off */
-  UVB_KNOB_PROLOGUE_PAIR = 5, /* 1: token-pair q/k prologue kernel (default); 0: one row per warp group */
+  UVB_KNOB_PROLOGUE_PAIR = 5, /* q AND k given: 2 = streaming kernel, persistent CTAs + bulk-copy ring (default, widths
+                                 1536 / 3072 / 5120); 1 = token-pair kernel; 0 = one row per warp group */
   UVB_KNOB_FMHA_POLY = 6,     /* lab builds only: one exp2 pair in every n (2, 3, 4) on the FMA pipe; 0 (default, shipped) = MUFU only */
   UVB_KNOB_SP_WAIT_TIMEOUT_S = 7, /* seconds uvb_sp_wait spins for a peer's hand-off flag before it traps (default 600,
                                      like an NCCL collective under torch.distributed); 0 = wait for ever */

@@ -67,6 +67,46 @@ def test_qk_norm_rope_matches_oracle(ext, heads, dtype):
         _bf16_close(got, want)
 
 
+@pytest.mark.parametrize("heads,b,l,groups", [(12, 1, 1000, 1), (12, 2, 131, 1), (24, 1, 517, 1), (40, 1, 333, 1),
+                                              (12, 1, 259, 4), (40, 2, 77, 8), (12, 1, 3, 1)])
+def test_streaming_prologue_is_bit_identical_to_the_row_kernels(ext, heads, b, l, groups):
+    """uvb_set_knob(UVB_KNOB_PROLOGUE_PAIR, 2): the persistent bulk-copy-ring kernel.  Same arithmetic, same rounding
+    points: bit-identical to the one-row-per-warp-group kernel (knob 0), which the test above pins to the oracle.
+    Shapes: every product width (1536 / 3072 / 5120), ragged last stage, padding tokens, more and fewer rows than one
+    stage per SM, and the Ulysses send layout (groups > 1) with a rank offset."""
+    dev = "cuda"
+    g = torch.Generator().manual_seed(heads * 100 + l)
+    dim = heads * 128
+    q = torch.randn(b, l, dim, generator=g).to(torch.bfloat16).to(dev)
+    k = (0.5 * torch.randn(b, l, dim, generator=g)).to(torch.bfloat16).to(dev)
+    wq, wk = (1 + 0.1 * torch.randn(dim, generator=g)).to(dev), (1 + 0.1 * torch.randn(dim, generator=g)).to(dev)
+    _, cs = _cos_sin(dev)
+    grid = [(max(1, (l - 2) // 12), 3, 4)] * b            # a few unrotated padding tokens at the end
+    kw = dict(cos_sin=cs, grid_sizes=grid, groups=groups, tok_offset=5 if groups > 1 else 0)
+    outs = {}
+    for mode in (0, 1, 2):
+        old = ext.set_knob("prologue_pair", mode)
+        try:
+            outs[mode] = ext.qk_norm_rope(q, k, wq, wk, 1e-6, heads, **kw)
+        finally:
+            ext.set_knob("prologue_pair", old)
+    torch.cuda.synchronize()
+    for mode in (1, 2):
+        assert torch.equal(outs[mode][0], outs[0][0]) and torch.equal(outs[mode][1], outs[0][1]), mode
+    # rotation only (qk_norm=False)
+    old = ext.set_knob("prologue_pair", 2)
+    try:
+        a = ext.qk_norm_rope(q, k, None, None, 1e-6, heads, **kw)
+    finally:
+        ext.set_knob("prologue_pair", old)
+    old = ext.set_knob("prologue_pair", 0)
+    try:
+        r = ext.qk_norm_rope(q, k, None, None, 1e-6, heads, **kw)
+    finally:
+        ext.set_knob("prologue_pair", old)
+    assert torch.equal(a[0], r[0]) and torch.equal(a[1], r[1])
+
+
 def test_qk_norm_without_rope_and_without_norm(ext):
     dev = "cuda"
     g = torch.Generator().manual_seed(5)

@@ -60,7 +60,7 @@ int g_knobs[UVB_KNOB_COUNT] = {
     /* UVB_KNOB_GEMM_CTAS     */ 2,   // 2 = CTA pairs (cta_group::2), 1 = single CTAs
     /* UVB_KNOB_GEMM_BN       */ 0,   // 0 = per-problem choice, 192 | 256 pins the tile width
     /* UVB_KNOB_GEMM_SMALL    */ 1,   // single-wave 128x64 tiles for small problems
-    /* UVB_KNOB_PROLOGUE_PAIR */ 1,   // token-pair prologue kernel when q and k are both given
+    /* UVB_KNOB_PROLOGUE_PAIR */ 2,   // q and k both given: 2 streaming kernel (bulk-copy ring), 1 token-pair kernel, 0 row kernel
     /* UVB_KNOB_FMHA_POLY     */ 0,   // CTA-pair attention kernel: 1 exp2 pair in every n on the FMA pipe (0, 2, 3, 4)
     /* UVB_KNOB_SP_WAIT_TIMEOUT_S */ 600,   // seconds a rank waits for a peer's hand-off flag before trapping; 0 = for ever
 };
@@ -456,9 +456,9 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
       return UVB_OK;
     };
     switch (dim) {
-      case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers>, uvb::StreamSmem<6, 1>::kDynBytes, 8);
-      case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers>, uvb::StreamSmem<6, 2>::kDynBytes, 4);
-      default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers>, uvb::StreamSmem<5, 4>::kDynBytes, 2);
+      case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers>, uvb::StreamSmem<6, 1>::kDynBytes, uvb::StreamSmem<6, 1>::kRows);
+      case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers>, uvb::StreamSmem<6, 2>::kDynBytes, uvb::StreamSmem<6, 2>::kRows);
+      default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers>, uvb::StreamSmem<5, 4>::kDynBytes, uvb::StreamSmem<5, 4>::kRows);
     }
   }
   const bool pair = g_knobs[UVB_KNOB_PROLOGUE_PAIR] != 0 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&

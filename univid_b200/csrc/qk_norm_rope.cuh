@@ -412,12 +412,12 @@ qk_norm_rope_pair_kernel(const __grid_constant__ NormRopeParams p) {
 //                copies (cp.async.bulk, complete_tx on an mbarrier) -- a stage holds the q rows and the k rows of
 //                R = 8 / WPR consecutive tokens, which are contiguous in [B, L, dim], i.e. TWO copies per stage;
 //                ~150-200 KB per SM are in flight at any time regardless of what the compute warps do;
-//   warps 0-7    consumers: WPR warps per token; the row is read from shared memory and unpacked ONCE (registers are
+//   warps 0-15   consumers: WPR warps per token; the row is read from shared memory and unpacked ONCE (registers are
 //                plentiful at one CTA per SM), the norm weights sit in shared memory, the token's (cos, sin) pairs are
 //                fetched once for q and k.
 // The arithmetic (order of operations, rounding points) is that of norm_rope_row: results are bit-identical.
 // ----------------------------------------------------------------------------------------------
-constexpr int kStreamConsumerWarps = 8;
+constexpr int kStreamConsumerWarps = 16;
 constexpr int kStreamThreads = (kStreamConsumerWarps + 1) * 32;
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
