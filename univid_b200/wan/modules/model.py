@@ -289,7 +289,65 @@ class WanSelfAttention(_DropOperandsOnApply, nn.Module):
         return self._out_proj(x)
 
 
+def _tensor_key(t):
+    return (id(t), t.data_ptr(), _version_of(t), tuple(t.shape), t.dtype, t.device)
+
+
+def _weights_key(*mods):
+    out = []
+    for m in mods:
+        for prm in (getattr(m, 'weight', None), getattr(m, 'bias', None)):
+            out.append(None if prm is None else (id(prm), prm.data_ptr(), _version_of(prm)))
+    return tuple(out)
+
+
 class WanCrossAttention(WanSelfAttention):
+    # The context (text embedding of the prompt) is the SAME tensor in every one of the ~100 DiT calls of a sampling
+    # run (two of them with classifier-free guidance), and so are the weights: its k / v projections -- and for the
+    # fused text weighting the bias-free projections and the biases -- are computed once per (context tensor, weights)
+    # and reused.  Keyed on tensor identity + version, so a context that is rebuilt per call
+    # (e.g. pre-scaled by the reference's hook) simply misses.  At most `context_cache_size` contexts per module.
+    context_cache_size = 2
+
+    def _context_side(self, context, fused):
+        """Cached context-side operands: ('plain': k normed [B, L2, N, 128] bf16, v [B, L2, N, 128] bf16) or
+        ('fused': bias-free k projection bf16 [B, L2, C], bias-free v projection fp32 [B, L2, C], b_k, b_v fp32)."""
+        cacheable = (self.context_cache_size > 0 and not torch.is_grad_enabled()
+                     and type(self.k) is nn.Linear and type(self.v) is nn.Linear)
+        key = None
+        if cacheable:
+            key = (fused, _tensor_key(context), _weights_key(self.k, self.v, self.norm_k),
+                   torch.is_autocast_enabled('cuda'))
+            cache = self.__dict__.setdefault('_uvb_ctx_cache', {})
+            hit = cache.get(key)
+            if hit is not None and hit[0]() is context:
+                return hit[1]
+        b, n, d = context.size(0), self.num_heads, self.head_dim
+        if not fused:
+            _, k = self._prologue(None, _lin(self.k, context), None, None)
+            v = _lin(self.v, context).view(b, -1, n, d)
+            if v.dtype != torch.bfloat16:
+                v = v.to(torch.bfloat16)
+            val = (k, v)
+        else:
+            # k(w*c) = w*(k(c) - b_k) + b_k and v(w*c) = w*(v(c) - b_v) + b_v: run the projections on the
+            # unscaled context (as modules, so LoRA wrappers stay in the loop) and recover the biases as
+            # the image of zero.
+            zero = context.new_zeros(1, 1, context.size(-1))
+            b_k, b_v = _lin(self.k, zero).flatten().float(), _lin(self.v, zero).flatten().float()
+            k_lin = (_lin(self.k, context).float() - b_k).to(torch.bfloat16).contiguous()
+            v_lin = _lin(self.v, context).float() - b_v
+            val = (k_lin, v_lin, b_k, b_v)
+        if cacheable:
+            if len(cache) >= 2 * self.context_cache_size:
+                for old in list(cache.keys())[:len(cache) - 2 * self.context_cache_size + 1]:
+                    del cache[old]
+            cache[key] = (weakref.ref(context), val)
+        return val
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_uvb_ctx_cache', None)
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x, context, context_lens, text_weight=1.0, text_len=0):
         r"""
@@ -308,32 +366,40 @@ class WanCrossAttention(WanSelfAttention):
         fused = text_weight != 1.0 and text_len > 0
         q, _ = self._prologue(_lin(self.q, x), None, None, None)
         if not fused:
-            _, k = self._prologue(None, _lin(self.k, context), None, None)
-            v = _lin(self.v, context).view(b, -1, n, d)
-            if v.dtype != torch.bfloat16:
-                v = v.to(torch.bfloat16)
+            k, v = self._context_side(context, False)
             lk = k.size(1)
             x = _ext.fmha_fwd(q, k, v, k_lens=_k_lens_arg(context_lens, b, lk, x.device))
             return self._out_proj(x)
 
-        # k(w*c) = w*(k(c) - b_k) + b_k and v(w*c) = w*(v(c) - b_v) + b_v: run the projections on the
-        # unscaled context (as modules, so LoRA wrappers stay in the loop) and recover the biases as
-        # the image of zero.
-        lk = context.size(1)
-        zero = context.new_zeros(1, 1, context.size(-1))
-        b_k, b_v = _lin(self.k, zero).flatten().float(), _lin(self.v, zero).flatten().float()
-        w_vec = torch.ones(lk, dtype=torch.float32, device=x.device)
-        w_vec[:text_len] = float(text_weight)
-        k_lin = (_lin(self.k, context).float() - b_k).to(torch.bfloat16)
-        # out = sum_j p_j (w_j l_j + b_v) = sum_j p_j (w_j l_j) + b_v: the weight rides on the 512 bias-free
-        # value rows (one tiny elementwise op) instead of on every probability inside the attention kernel
-        v_lin = ((_lin(self.v, context).float() - b_v) * w_vec.view(1, lk, 1)).to(torch.bfloat16).view(b, lk, n, d)
         wk, eps_k, pre_k = _norm_weight(self.norm_k)
         if pre_k is not None:
             raise NotImplementedError('fused text weighting needs a WanRMSNorm or Identity norm_k')
-        _, k = _ext.qk_norm_rope(None, k_lin.contiguous(), None, wk, eps_k, n, row_scale=w_vec, pre_bias=b_k)
-        x = _ext.fmha_fwd(q, k, v_lin, k_lens=_k_lens_arg(context_lens, b, lk, x.device), out_bias=b_v)
+        lk = context.size(1)
+        k_lin, v_lin, b_k, b_v = self._context_side(context, True)
+        w_vec = _weight_vector(lk, int(text_len), float(text_weight), x.device)
+        # out = sum_j p_j (w_j l_j + b_v) = sum_j p_j (w_j l_j) + b_v: the weight rides on the 512 bias-free
+        # value rows (one tiny elementwise op) instead of on every probability inside the attention kernel
+        v_w = (v_lin * w_vec.view(1, lk, 1)).to(torch.bfloat16).view(b, lk, n, d)
+        _, k = _ext.qk_norm_rope(None, k_lin, None, wk, eps_k, n, row_scale=w_vec, pre_bias=b_k)
+        x = _ext.fmha_fwd(q, k, v_w, k_lens=_k_lens_arg(context_lens, b, lk, x.device), out_bias=b_v)
         return self._out_proj(x)
+
+
+_WEIGHT_VECTORS = {}
+
+
+def _weight_vector(lk, text_len, weight, device):
+    """fp32 [lk]: `weight` on the first text_len rows, 1 elsewhere; cached per value (a sampling run revisits the same
+    ~40 weights in every layer)."""
+    key = (lk, text_len, weight, str(device))
+    v = _WEIGHT_VECTORS.get(key)
+    if v is None:
+        v = torch.ones(lk, dtype=torch.float32, device=device)
+        v[:text_len] = weight
+        if len(_WEIGHT_VECTORS) > 256:
+            _WEIGHT_VECTORS.clear()
+        _WEIGHT_VECTORS[key] = v
+    return v
 
 
 class WanAttentionBlock(_DropOperandsOnApply, nn.Module):
@@ -551,13 +617,38 @@ class WanModel(nn.Module):
             e0 = self.time_projection(e).unflatten(2, (6, self.dim))
             assert e.dtype == torch.float32 and e0.dtype == torch.float32
 
-        context = self.text_embedding(
-            torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
+        context = self._embed_context(context)
         kwargs = dict(e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=context,
                       context_lens=None)
         if e_index is not None:
             kwargs['e_index'] = e_index
         return x, e, kwargs
+
+    def _embed_context(self, context):
+        """text_embedding of the padded prompt embeddings (model.py:473-478).  A sampling run calls the DiT ~100 times
+        with the same one or two prompt tensors: the embedded context is computed once per (input tensors, weights) and
+        the SAME tensor object is handed to the blocks every time, which is what lets WanCrossAttention reuse its
+        context-side projections.  Inference only; at most 4 prompts are remembered."""
+        cacheable = not torch.is_grad_enabled() and all(torch.is_tensor(u) for u in context)
+        key = None
+        if cacheable:
+            key = (tuple(_tensor_key(u) for u in context), _weights_key(self.text_embedding[0], self.text_embedding[2]),
+                   torch.is_autocast_enabled('cuda'), torch.get_autocast_dtype('cuda'))
+            cache = self.__dict__.setdefault('_uvb_text_cache', {})
+            hit = cache.get(key)
+            if hit is not None and all(r() is u for r, u in zip(hit[0], context)):
+                return hit[1]
+        out = self.text_embedding(
+            torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
+        if cacheable:
+            if len(cache) >= 4:
+                del cache[next(iter(cache))]
+            cache[key] = ([weakref.ref(u) for u in context], out)
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_uvb_text_cache', None)
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x, t, context, seq_len, y=None):
         r"""
