@@ -223,6 +223,15 @@ enum uvb_act { UVB_ACT_NONE = 0, UVB_ACT_GELU_TANH = 1 };
 int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
                     int64_t ldw, int64_t ldy, int act, void* stream);
 
+/* The same GEMM with the output scattered by column groups: columns [j * N/n_peers, (j + 1) * N/n_peers) of the result
+ * are TMA-stored as a [M, N/n_peers] matrix (leading dimension ld_peer) at y_peers[j].  Replaces: the v projection
+ * (model.py:139) followed by the head-chunk pack of all_to_all (distributed/util.py:27) in the sequence-parallel
+ * self-attention (distributed/sequence_parallel.py:147-176): y_peers[j] is this rank's slot inside rank j's exchange
+ * buffer (mapped over NVLink), so the projection's epilogue IS the first half of the Ulysses exchange of v.
+ * N/n_peers must be a multiple of 64; y_peers is a HOST array of n_peers (<= 8) device pointers. */
+int uvb_linear_bf16_sp(const void* x, const void* w, const float* bias, void* const* y_peers, int n_peers, int M, int N,
+                       int K, int64_t ldx, int64_t ldw, int64_t ld_peer, int act, void* stream);
+
 /* Sampler update between two DiT forwards, one fused elementwise pass.
  * Replaces: the classifier-free-guidance combine `uncond + g * (cond - uncond)` (models/wan/textimage2video.py:385-386)
  * and FlowUniPCMultistepScheduler.step (models/wan/utils/fm_solvers_unipc.py:657-741: convert_model_output :320-323,

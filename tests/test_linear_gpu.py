@@ -151,3 +151,25 @@ def test_ffn_fused_gelu_matches_module():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         x = torch.randn(5, 64, device="cuda")
         assert torch.equal(mdl._ffn_forward(exact, x), exact(x))
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(300, 1024, 256, 4), (1000, 1536, 1536, 2), (257, 5120, 512, 8), (4000, 1536, 512, 4)])
+def test_linear_column_group_scatter_equals_linear_plus_head_scatter(M, N, K, groups):
+    """uvb_linear_bf16_sp: the GEMM epilogue stores column group j ([M, N/groups]) through its own pointer -- on one
+    GPU the 'peers' are local buffers laid out like the Ulysses exchange slots ([B=1, p, s, n, 128] with the slot of
+    'rank' 1) -- bit-identical to uvb_linear_bf16 followed by the head scatter."""
+    from univid_b200 import _ext
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(1, M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = (0.5 * torch.randn(N, generator=g)).to(torch.bfloat16).float().cuda()
+    n = N // groups // 128
+    want = _ext.head_scatter(_ext.linear(x, w, b).view(1, M, N // 128, 128), groups)          # [groups, 1, M, n, 128]
+    p, slot = 3, 1                                                                             # 3 "ranks", we are rank 1
+    recv = [torch.full((1, p, M, n, 128), float("nan"), dtype=torch.bfloat16, device="cuda") for _ in range(groups)]
+    ptrs = _ext.ptr_array([r.data_ptr() + slot * M * n * 128 * 2 for r in recv])
+    assert _ext.linear(x, w, b, peers=(ptrs, groups, n * 128)) is None
+    torch.cuda.synchronize()
+    for j in range(groups):
+        assert torch.equal(recv[j][0, slot], want[j, 0]), j
+        assert torch.isnan(recv[j][0, 0].float()).all() and torch.isnan(recv[j][0, 2].float()).all()   # other slots untouched

@@ -92,7 +92,13 @@ def test_sp_attention_matches_the_oracle(world, transport, case):
         pytest.skip(f"needs {world} GPUs")
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out, transport, case), nprocs=world, join=True)
+    for attempt in range(3):               # a port picked as free can be taken by the time the store binds it
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), out, transport, case), nprocs=world, join=True)
+            break
+        except Exception as e:             # noqa: BLE001 -- ProcessRaisedException carries the child's traceback as text
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
     dim, heads, L, _, _ = CASES[case]
     freqs = orc.make_freqs(128)
     for layer in range(3):

@@ -17,6 +17,7 @@ EXPORTS = (
     "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step", "uvb_set_knob", "uvb_get_knob",
+    "uvb_linear_bf16_sp",
 )
 ABI_VERSION = 108
 KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
@@ -90,6 +91,8 @@ def lib():
     L.uvb_block_glue.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _vp, _f, _i, _vp]
     L.uvb_linear_bf16.restype = _i
     L.uvb_linear_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
+    L.uvb_linear_bf16_sp.restype = _i
+    L.uvb_linear_bf16_sp.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i, _vp]
     L.uvb_unipc_step.restype = _i
     L.uvb_unipc_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _c.POINTER(UnipcCoef), _vp]
     L.uvb_set_knob.restype = _i
@@ -447,10 +450,13 @@ def block_glue(x, y=None, gate=None, ln=None, scale=None, shift=None, eps=1e-6, 
 ACT_NONE, ACT_GELU_TANH = 0, 1
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, out=None):
+def linear(x, weight, bias=None, act=ACT_NONE, out=None, peers=None):
     """y = act(x @ weight.T + bias) (uvb_linear_bf16): x bf16 [..., K] with dense rows, weight bf16 [N, K]
     (nn.Linear layout), bias fp32 [N] (already rounded to bf16 values when mirroring autocast) or None.
-    Returns bf16 [..., N]."""
+    Returns bf16 [..., N].
+    peers = (ptrs, n, ld): column group j of the result ([M, N/n]) is stored through ptrs[j] with leading dimension
+    ld instead (uvb_linear_bf16_sp: the projection's epilogue writes the Ulysses send layout into the peers'
+    buffers); nothing is returned."""
     global launch_count
     _require_cuda(x, weight, bias)
     _no_grad_only(x, weight, bias)
@@ -471,6 +477,13 @@ def linear(x, weight, bias=None, act=ACT_NONE, out=None):
         if bias.numel() != N:
             raise ValueError("linear: bias must have N entries")
         bias = (bias if bias.dtype == torch.float32 else bias.float()).contiguous()
+    if peers is not None:
+        ptrs, n_peers, ld = peers
+        if M > 0:
+            _check(lib().uvb_linear_bf16_sp(_ptr(x2), _ptr(weight), _ptr(bias), _c.cast(ptrs, _vp), int(n_peers), M, N, K,
+                                            x2.stride(0), weight.stride(0), int(ld), int(act), _stream(x)))
+            launch_count += 1
+        return None
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
     elif out.dtype != torch.bfloat16 or out.numel() != M * N or not out.is_contiguous():

@@ -128,14 +128,30 @@ int make_matrix_map(CUtensorMap* tm, const void* base, int rows, int cols, int64
   return UVB_OK;
 }
 
+// column-group scatter destinations of a GEMM launch (see GemmParams::n_peers)
+struct GemmPeers {
+  void* const* ptrs = nullptr;
+  int n = 0;
+  int64_t ld = 0;
+};
+
 template <int kCtas, int kBN>
 int launch_gemm(uvb::GemmParams& p, const void* x, const void* w, void* y, int64_t ldx, int64_t ldw, int64_t ldy,
-                int workers, cudaStream_t stream) {
+                int workers, cudaStream_t stream, const GemmPeers& peers = GemmPeers()) {
   using SM = uvb::GemmSmem<kCtas, kBN>;
   int rc;
   if ((rc = make_matrix_map(&p.tm_a, x, p.M, p.K, ldx, uvb::kGemmBM)) != UVB_OK) return rc;
   if ((rc = make_matrix_map(&p.tm_b, w, p.N, p.K, ldw, kBN / kCtas)) != UVB_OK) return rc;
-  if ((rc = make_matrix_map(&p.tm_c, y, p.M, p.N, ldy, uvb::kGemmBM)) != UVB_OK) return rc;
+  if (peers.n == 0) {
+    if ((rc = make_matrix_map(&p.tm_c, y, p.M, p.N, ldy, uvb::kGemmBM)) != UVB_OK) return rc;
+  } else {
+    p.n_peers = peers.n;
+    p.peer_cols = p.N / peers.n;
+    for (int j = 0; j < peers.n; ++j) {
+      if ((rc = make_matrix_map(&p.tm_c_peer[j], peers.ptrs[j], p.M, p.peer_cols, peers.ld, uvb::kGemmBM)) != UVB_OK)
+        return rc;
+    }
+  }
   p.n_m = (p.M + uvb::kGemmBM * kCtas - 1) / (uvb::kGemmBM * kCtas);
   p.n_n = (p.N + kBN - 1) / kBN;
   const long long tiles = static_cast<long long>(p.n_m) * p.n_n;
@@ -505,6 +521,42 @@ int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
   return p.n_peers > 0 ? launch_norm_rope_t<InT, true>(p, stream) : launch_norm_rope_t<InT, false>(p, stream);
 }
 
+int linear_impl(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx, int64_t ldw,
+                int64_t ldy, int act, void* stream, const GemmPeers& peers) {
+  if (x == nullptr || w == nullptr) return fail(UVB_ERR_INVALID, "null matrix pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return fail(UVB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
+  if (N % 8 != 0 || K % 8 != 0) return fail(UVB_ERR_INVALID, "N=%d and K=%d must be multiples of 8", N, K);
+  if (act != UVB_ACT_NONE && act != UVB_ACT_GELU_TANH) return fail(UVB_ERR_INVALID, "bad activation %d", act);
+  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 3) != 0) return fail(UVB_ERR_INVALID, "bias alignment");
+  int rc = check_device();
+  if (rc != UVB_OK) return rc;
+  int sms = 0;
+  if ((rc = sm_count(&sms)) != UVB_OK) return rc;
+  uvb::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.act = act;
+  const int ctas = g_knobs[UVB_KNOB_GEMM_CTAS] == 1 ? 1 : 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int workers = 0;
+  // Small problems (the 512 context rows of the cross-attention k / v projections, single-row probes): when 128 x 64
+  // tiles of single CTAs fit in ONE wave, latency is what counts -- many small tiles instead of a dozen 256-wide pairs.
+  const bool allow_small = g_knobs[UVB_KNOB_GEMM_SMALL] != 0;
+  const long long small_tiles = static_cast<long long>((M + uvb::kGemmBM - 1) / uvb::kGemmBM) * ((N + 63) / 64);
+  if (allow_small && small_tiles <= sms) return launch_gemm<1, 64>(p, x, w, y, ldx, ldw, ldy, sms, st, peers);
+  if (ctas == 2) {
+    if ((rc = gemm_workers<2>(sms, &workers)) != UVB_OK) return rc;
+    return pick_tile_n<2>(p, workers) == 192 ? launch_gemm<2, 192>(p, x, w, y, ldx, ldw, ldy, workers, st, peers)
+                                             : launch_gemm<2, 256>(p, x, w, y, ldx, ldw, ldy, workers, st, peers);
+  }
+  if ((rc = gemm_workers<1>(sms, &workers)) != UVB_OK) return rc;
+  return pick_tile_n<1>(p, workers) == 192 ? launch_gemm<1, 192>(p, x, w, y, ldx, ldw, ldy, workers, st, peers)
+                                           : launch_gemm<1, 256>(p, x, w, y, ldx, ldw, ldy, workers, st, peers);
+}
+
 }  // namespace
 
 extern "C" {
@@ -808,38 +860,23 @@ int uvb_xattn_fwd_bf16(const void* q, const void* k, const void* v, void* o, con
 
 int uvb_linear_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
                     int64_t ldw, int64_t ldy, int act, void* stream) {
-  if (x == nullptr || w == nullptr || y == nullptr) return fail(UVB_ERR_INVALID, "null matrix pointer");
-  if (M <= 0 || N <= 0 || K <= 0) return fail(UVB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
-  if (N % 8 != 0 || K % 8 != 0) return fail(UVB_ERR_INVALID, "N=%d and K=%d must be multiples of 8", N, K);
-  if (act != UVB_ACT_NONE && act != UVB_ACT_GELU_TANH) return fail(UVB_ERR_INVALID, "bad activation %d", act);
-  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 3) != 0) return fail(UVB_ERR_INVALID, "bias alignment");
-  int rc = check_device();
-  if (rc != UVB_OK) return rc;
-  int sms = 0;
-  if ((rc = sm_count(&sms)) != UVB_OK) return rc;
-  uvb::GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.bias = bias;
-  p.M = M;
-  p.N = N;
-  p.K = K;
-  p.act = act;
-  const int ctas = g_knobs[UVB_KNOB_GEMM_CTAS] == 1 ? 1 : 2;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int workers = 0;
-  // Small problems (the 512 context rows of the cross-attention k / v projections, single-row probes): when 128 x 64
-  // tiles of single CTAs fit in ONE wave, latency is what counts -- many small tiles instead of a dozen 256-wide pairs.
-  const bool allow_small = g_knobs[UVB_KNOB_GEMM_SMALL] != 0;
-  const long long small_tiles = static_cast<long long>((M + uvb::kGemmBM - 1) / uvb::kGemmBM) * ((N + 63) / 64);
-  if (allow_small && small_tiles <= sms) return launch_gemm<1, 64>(p, x, w, y, ldx, ldw, ldy, sms, st);
-  if (ctas == 2) {
-    if ((rc = gemm_workers<2>(sms, &workers)) != UVB_OK) return rc;
-    return pick_tile_n<2>(p, workers) == 192 ? launch_gemm<2, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)
-                                             : launch_gemm<2, 256>(p, x, w, y, ldx, ldw, ldy, workers, st);
+  if (y == nullptr) return fail(UVB_ERR_INVALID, "null matrix pointer");
+  return linear_impl(x, w, bias, y, M, N, K, ldx, ldw, ldy, act, stream, GemmPeers());
+}
+
+int uvb_linear_bf16_sp(const void* x, const void* w, const float* bias, void* const* y_peers, int n_peers, int M, int N,
+                       int K, int64_t ldx, int64_t ldw, int64_t ld_peer, int act, void* stream) {
+  if (y_peers == nullptr || n_peers <= 0 || n_peers > uvb::kMaxPeers) return fail(UVB_ERR_INVALID, "bad peer list");
+  if (N % n_peers != 0 || (N / n_peers) % 64 != 0)
+    return fail(UVB_ERR_INVALID, "N=%d must split into %d column groups of a multiple of 64 columns", N, n_peers);
+  for (int j = 0; j < n_peers; ++j) {
+    if (y_peers[j] == nullptr) return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
   }
-  if ((rc = gemm_workers<1>(sms, &workers)) != UVB_OK) return rc;
-  return pick_tile_n<1>(p, workers) == 192 ? launch_gemm<1, 192>(p, x, w, y, ldx, ldw, ldy, workers, st)
-                                           : launch_gemm<1, 256>(p, x, w, y, ldx, ldw, ldy, workers, st);
+  GemmPeers peers;
+  peers.ptrs = y_peers;
+  peers.n = n_peers;
+  peers.ld = ld_peer;
+  return linear_impl(x, w, bias, nullptr, M, N, K, ldx, ldw, 0, act, stream, peers);
 }
 
 int uvb_unipc_step(const float* cond, const float* uncond, const float* x, const float* last, const float* m0,

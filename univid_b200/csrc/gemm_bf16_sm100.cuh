@@ -59,6 +59,13 @@ struct GemmParams {
   int n_m;            // row tiles of (128 * kCtas) rows
   int n_n;            // column tiles of kBN
   int group_n;        // column tiles walked per row tile (rasterisation)
+  // Column-group scatter (Ulysses: the v projection stored straight into the peers' exchange buffers, the
+  // chunk(...).contiguous() pack of distributed/util.py:27 fused into the GEMM epilogue): when n_peers > 0 the
+  // output columns [j * peer_cols, (j + 1) * peer_cols) go to tm_c_peer[j] (a [M, peer_cols] matrix in rank j's
+  // buffer, mapped over NVLink) instead of tm_c.  peer_cols is a multiple of 64, so a staging panel never straddles.
+  int n_peers;
+  int peer_cols;
+  CUtensorMap tm_c_peer[8];
 };
 
 // ---- 2-D TMA and cluster helpers local to the GEMM ----
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
-    tma_prefetch_desc(&p.tm_c);
+    if (p.n_peers == 0) tma_prefetch_desc(&p.tm_c);
   }
   tc_fence_before();
   if constexpr (kCtas == 2) {
@@ -340,7 +347,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (et == 0) {
-          if (col0 + j * 64 < p.N && row0 < p.M) tma_store_2d(&p.tm_c, panel, col0 + j * 64, row0);
+          if (col0 + j * 64 < p.N && row0 < p.M) {
+            if (p.n_peers == 0) {
+              tma_store_2d(&p.tm_c, panel, col0 + j * 64, row0);
+            } else {
+              // static indices only: the descriptor must stay a plain param-space address
+              const int c = col0 + j * 64;
+              const int peer = c / p.peer_cols;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (q == peer) tma_store_2d(&p.tm_c_peer[q], panel, c - q * p.peer_cols, row0);
+              }
+            }
+          }
           tma_store_commit();
         }
       }

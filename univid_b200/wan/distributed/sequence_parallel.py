@@ -12,7 +12,7 @@ write local send buffers and the exchange is three NCCL all-to-alls in and one o
 import torch
 
 from ... import _ext
-from ..modules.model import _cos_sin_table, _lin, sinusoidal_embedding_1d  # noqa: F401
+from ..modules.model import _cos_sin_table, _lin, _lin_to_peers, sinusoidal_embedding_1d  # noqa: F401
 from . import p2p
 from ..modules.attention import _k_lens_arg
 from .ulysses import attend_exchanged, distributed_attention  # noqa: F401
@@ -93,16 +93,21 @@ def sp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16):
         return type(self).forward(self, x, seq_lens, grid_sizes, freqs)
     if n % world != 0:
         raise ValueError(f'{n} heads cannot be split over {world} ranks')
-    v = _lin(self.v, x).view(b, s, n, d)
-    if v.dtype != torch.bfloat16:
-        v = v.to(torch.bfloat16)
     ctx = p2p.context(b, s, n, x.device)
     if ctx is not None:
         ctx.next_epoch()
+        # v: the projection's epilogue TMA-stores every head group into its rank's exchange buffer (B == 1); q and k
+        # go through the fused norm + RoPE prologue, which stores the same way
+        if not _lin_to_peers(self.v, x, (ctx.v_peers, world, ctx.send_sl)):
+            v = _lin(self.v, x).view(b, s, n, d)
+            v = v if v.dtype == torch.bfloat16 else v.to(torch.bfloat16)
+            _ext.head_scatter(v.contiguous(), world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
         self._prologue(_lin(self.q, x), _lin(self.k, x), _cos_sin_table(freqs, x.device), grid_sizes, tok_offset=rank * s,
                        groups=world, peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
-        _ext.head_scatter(v.contiguous(), world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
         return self._out_proj(ctx.attend(_k_lens_arg(seq_lens, b, world * s, x.device)))
+    v = _lin(self.v, x).view(b, s, n, d)
+    if v.dtype != torch.bfloat16:
+        v = v.to(torch.bfloat16)
     q_send, k_send = self._prologue(_lin(self.q, x), _lin(self.k, x), _cos_sin_table(freqs, x.device), grid_sizes,
                                     tok_offset=rank * s, groups=world)
     v_send = _ext.head_scatter(v.contiguous(), world)

@@ -202,6 +202,16 @@ def _gemm_ok(mod, x):
     return mod.weight.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
 
 
+def _lin_to_peers(mod, x, peers):
+    """mod(x) with the result scattered by column groups into the peers' buffers (uvb_linear_bf16_sp); False when the
+    projection cannot take the GEMM route (the caller then projects and scatters separately)."""
+    if not _gemm_ok(mod, x) or x.dim() != 3 or x.size(0) != 1 or (mod.out_features // peers[1]) % 64 != 0:
+        return False
+    w, b = _linear_operands(mod)
+    _ext.linear(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), w, b, peers=peers)
+    return True
+
+
 def _lin(mod, x, act=_ext.ACT_NONE):
     """mod(x) for a projection module (optionally followed by tanh-GELU when act is set: the caller has
     checked that the activation module is nn.GELU(approximate='tanh'))."""
