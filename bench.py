@@ -604,6 +604,11 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
 def run_native_arm(args, cfg_key):
     env = Env(args)
     cfg = CONFIGS[cfg_key]
+    if args.knob:
+        from univid_b200 import _ext
+        for kv in args.knob:
+            name, value = kv.split("=")
+            _ext.set_knob(name, int(value))
     main = measure(env, args, cfg_key, args.steps, args.warmup, denoise=not args.skip_denoise)
     subs = {}
     if not args.no_sub_records and cfg_key == HEADLINE:
@@ -637,6 +642,8 @@ def run_native_arm(args, cfg_key):
             "roofline_gemm": main.get("roofline_gemm"), "kernel_split": main.get("kernel_split"),
             "configs": subs, "cpu_baseline": cpu,
         }
+        if args.knob:
+            line["knobs"] = args.knob
         print(json.dumps(line))
     if env.world > 1:
         env.dist.destroy_process_group()
@@ -758,6 +765,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--skip-denoise", action="store_true", help="omit the full WanModel denoise-step timing")
     ap.add_argument("--no-sub-records", action="store_true", help="omit the 1.3B and text-weight-sweep sub-records")
+    ap.add_argument("--knob", action="append", default=[], metavar="NAME=VALUE",
+                    help="A/B runs only: uvb_set_knob before measuring (e.g. fmha_pair=0, prologue_pair=1); recorded in the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     cfg_key = args.config or HEADLINE

@@ -73,12 +73,15 @@ def main():
         if os.path.getsize(f) and "ncu_" not in os.path.basename(f):
             shutil.copy(f, dst)
 
-    lpath = os.path.join(src, f"launches_{tag}.csv")
-    if os.path.exists(lpath):
+    for lname, what in ((f"launches_{tag}.csv", "`bench.py --steps 2 --warmup 3 --skip-cpu --skip-denoise --no-sub-records` (headline config)"),
+                        (f"launches_1p3B_{tag}.csv", "`bench.py --config 1.3B --steps 2 --warmup 3 --skip-cpu --skip-denoise --no-sub-records`")):
+        lpath = os.path.join(src, lname)
+        if not os.path.exists(lpath):
+            continue
         shutil.copy(lpath, dst)
         agg = launch_summary(lpath)
         tot = sum(a[1] for a in agg.values())
-        lines.append(f"\n## ncu launch list of `bench.py --steps 2 --warmup 3 --skip-cpu --skip-denoise` (launches_{tag}.csv; cold-cache, serialised)\n")
+        lines.append(f"\n## ncu launch list of {what} ({lname}; cold-cache, serialised)\n")
         lines.append("| kernel | grid | launches | total ms | share | avg us |\n|---|---|---:|---:|---:|---:|")
         for (name, grid), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             lines.append(f"| `{name}` | {grid} | {n} | {t:.3f} | {100 * t / tot:.1f}% | {t / n * 1e3:.1f} |")
@@ -136,12 +139,19 @@ def main():
         tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         cur = json.load(open(tj)) if os.path.exists(tj) else {}
         for k, v in traffic.items():
-            if k.startswith("prof_fmha_"):
+            if k.startswith("prof_fmha14B_"):
+                cur.setdefault("14B", {})["fmha_dram_bytes_per_launch"] = v
+                cur["14B"]["source"] = f"profiles/{tag}/{k}_raw.csv"
+            elif k.startswith("prof_prol14B_"):
+                cur.setdefault("14B", {})["prologue_dram_bytes_per_launch"] = v
+            elif k.startswith("prof_fmha_single_"):
+                pass
+            elif k.startswith("prof_fmha_"):
                 cur.setdefault("1.3B", {})["fmha_dram_bytes_per_launch"] = v
                 cur["1.3B"]["source"] = f"profiles/{tag}/{k}_raw.csv"
-            if k.startswith("prof_prol_"):
+            elif k.startswith("prof_prol_"):
                 cur.setdefault("1.3B", {})["prologue_dram_bytes_per_launch"] = v
-            if k.startswith("prof_gemm_"):
+            elif k.startswith("prof_gemm_"):
                 cur.setdefault("1.3B", {})["gemm_ffn0_dram_bytes_per_launch"] = v
         json.dump(cur, open(tj, "w"), indent=1)
     open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(lines) + "\n")

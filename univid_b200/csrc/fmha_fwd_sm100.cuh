@@ -296,6 +296,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
   tc_fence_before();
   if constexpr (kCtas == 2) {
     cluster_sync_all();     // the peer's barriers are initialised and its TMEM is allocated
+    __syncthreads();        // (subsumed by the cluster barrier; spelled out for compute-sanitizer's racecheck, which
+                            // does not take barrier.cluster as ordering the tcgen05.alloc write of tmem_ptr)
   } else {
     __syncthreads();
   }
@@ -703,6 +705,11 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         mx1 = fmax3(mx1, __uint_as_float(sr[kBlockN - 2]), __uint_as_float(sr[kBlockN - 1]));
         const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
+        if constexpr (!kPSmem) {
+          // Without the shared-memory P panel nothing waits on pv_done unless a rescale happens; one non-blocking
+          // test per step keeps the barrier's phases observed (compute-sanitizer synccheck: "missing wait").
+          if (step > 0 && wq == 0 && lane == 0) (void)mbar_try_wait(&pv_done[t], par ^ 1);
+        }
         if (step == 0) {
           m = tile_max;
         } else {

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   tc_fence_before();
   if constexpr (kCtas == 2) {
     cluster_sync_all();
+    __syncthreads();        // subsumed by the cluster barrier; spelled out for compute-sanitizer's racecheck
   } else {
     __syncthreads();
   }
