@@ -30,6 +30,9 @@ cap() {  # name kernel-regex args...
   local name=$1 rx=$2; shift 2
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 1 -c 1 -f -o gpurun_out/prof_${name}_$TAG $T "$@" > gpurun_out/ncu_${name}_$TAG.log 2>&1
   tail -1 gpurun_out/ncu_${name}_$TAG.log
+  # gpurun copies back at most 64 MiB: keep the raw metric page (what the summaries are made of), drop the 15 MB report
+  ncu -i gpurun_out/prof_${name}_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${name}_${TAG}_rawpage.csv 2>/dev/null
+  rm -f gpurun_out/prof_${name}_$TAG.ncu-rep
 }
 cap fmha fmha_fwd_kernel fmha 1 32760 32760 12 -1 0 1
 cap fmha14B fmha_fwd_kernel fmha 1 75600 75600 40 -1 0 1

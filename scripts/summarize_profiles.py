@@ -33,7 +33,11 @@ KEYS = (
 
 
 def raw_metrics(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """Metrics of every launch in a .ncu-rep, or in the `--page raw --csv` dump made of it on the GPU box."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return []
@@ -117,8 +121,9 @@ def main():
         lines.append(f"| total | {sum(a[0] for a in agg.values())} | {tot:.3f} | |")
 
     traffic = {}
-    for rep in sorted(glob.glob(os.path.join(src, f"prof_*_{tag}.ncu-rep"))):
-        name = os.path.basename(rep)[:-len(".ncu-rep")]
+    for rep in sorted(glob.glob(os.path.join(src, f"prof_*_{tag}.ncu-rep")) + glob.glob(os.path.join(src, f"prof_*_{tag}_rawpage.csv"))):
+        name = os.path.basename(rep)
+        name = name[:-len(".ncu-rep")] if name.endswith(".ncu-rep") else name[:-len("_rawpage.csv")]
         for m in raw_metrics(rep):
             kn = m.get("Kernel Name", ("?", ""))[0]
             lines.append(f"\n## `ncu --set full` {name} -- `{kn}` grid {m.get('Grid Size', ('?', ''))[0]} block {m.get('Block Size', ('?', ''))[0]}\n")

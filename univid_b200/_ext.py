@@ -17,9 +17,9 @@ EXPORTS = (
     "uvb_qk_norm_rope_sp", "uvb_head_scatter_sp", "uvb_fmha_fwd_sp_bf16", "uvb_sp_buffer_alloc",
     "uvb_sp_buffer_free", "uvb_sp_ipc_export", "uvb_sp_ipc_import", "uvb_sp_ipc_close", "uvb_sp_signal",
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step", "uvb_set_knob", "uvb_get_knob",
-    "uvb_linear_bf16_sp",
+    "uvb_linear_bf16_sp", "uvb_sp_signal_wait",
 )
-ABI_VERSION = 108
+ABI_VERSION = 109
 KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
          "fmha_poly": 6, "sp_wait_timeout_s": 7}
 
@@ -67,9 +67,11 @@ def lib():
     _u32, _pp = _c.c_uint32, _c.POINTER(_c.c_void_p)
     L.uvb_qk_norm_rope_sp.restype = _i
     L.uvb_qk_norm_rope_sp.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
-                                      _vp, _i, _f, _i, _i64, _i64, _i64, _vp]
+                                      _vp, _i, _f, _i, _i64, _i64, _i64, _i, _i, _i, _vp]
     L.uvb_head_scatter_sp.restype = _i
-    L.uvb_head_scatter_sp.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp]
+    L.uvb_head_scatter_sp.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp]
+    L.uvb_sp_signal_wait.restype = _i
+    L.uvb_sp_signal_wait.argtypes = [_vp, _i, _u32, _vp, _vp]
     L.uvb_fmha_fwd_sp_bf16.restype = _i
     L.uvb_fmha_fwd_sp_bf16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f,
                                        _vp, _i64, _vp]
@@ -194,11 +196,14 @@ def ptr_array(ptrs):
 
 
 def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=None, tok_offset=0,
-                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None, peers=None):
+                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None, peers=None, head_range=None,
+                 max_ctas=0):
     """Fused RMSNorm (+RoPE) of q and/or k: [B, L, dim] -> bf16 [B, L, N, 128] (groups == 1) or the
     Ulysses send layout [groups, B, L, N/groups, 128].  See uvb_qk_norm_rope in the header.
     peers = (q_ptrs, k_ptrs, out_sb, out_sl): head group j is stored through q_ptrs[j] / k_ptrs[j]
-    (ctypes void*[groups] of peer-mapped device addresses, uvb_qk_norm_rope_sp) and nothing is returned."""
+    (ctypes void*[groups] of peer-mapped device addresses, uvb_qk_norm_rope_sp) and nothing is returned.
+    head_range = (lo, hi): with peers, store only the heads lo <= n % (N/groups) < hi (one phase of the exchange);
+    max_ctas caps the grid of the streaming kernel (0 = whole device)."""
     global launch_count
     ref = q_in if q_in is not None else k_in
     _require_cuda(q_in, k_in, wq, wk, cos_sin, row_scale, pre_bias)
@@ -230,7 +235,8 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
             _ptr(cos_sin), _ptr(row_scale), _ptr(pre_bias), None, None,
             None if q_in is None else _c.cast(q_ptrs, _vp), None if k_in is None else _c.cast(k_ptrs, _vp),
             groups, B, L, N, None if grid is None else _c.cast(grid, _vp), int(tok_offset), float(eps), hpg,
-            int(out_sb), int(out_sl), 0, _stream(ref)))
+            int(out_sb), int(out_sl), 0, 0 if head_range is None else int(head_range[0]),
+            hpg if head_range is None else int(head_range[1]), int(max_ctas), _stream(ref)))
         launch_count += 1
         return None, None
     q_out = _grouped_out(q_out, q_in, groups, B, L, hpg, ref.device)
@@ -254,9 +260,10 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
     return q_out, k_out
 
 
-def head_scatter(v, groups, out=None, peers=None):
+def head_scatter(v, groups, out=None, peers=None, head_range=None, max_ctas=0):
     """v [B, L, N, 128] bf16 -> [groups, B, L, N/groups, 128] (Ulysses send layout); with
-    peers = (ptrs, out_sb, out_sl) head group j is stored through ptrs[j] (uvb_head_scatter_sp)."""
+    peers = (ptrs, out_sb, out_sl) head group j is stored through ptrs[j] (uvb_head_scatter_sp); head_range /
+    max_ctas as in qk_norm_rope."""
     global launch_count
     _require_cuda(v)
     B, L, N, D = v.shape
@@ -266,7 +273,8 @@ def head_scatter(v, groups, out=None, peers=None):
     if peers is not None:
         ptrs, out_sb, out_sl = peers
         _check(lib().uvb_head_scatter_sp(_ptr(v), None, _c.cast(ptrs, _vp), groups, B, L, N, hpg, int(out_sb),
-                                         int(out_sl), 0, _stream(v)))
+                                         int(out_sl), 0, 0 if head_range is None else int(head_range[0]),
+                                         hpg if head_range is None else int(head_range[1]), int(max_ctas), _stream(v)))
         launch_count += 1
         return None
     out = _grouped_out(out, v, groups, B, L, hpg, v.device)
@@ -379,6 +387,12 @@ def fmha_fwd_sp(q, k, v, o_ptrs, n_peers, head_offset, total_heads, k_lens=None,
 def sp_signal(flag_ptrs, n, value, stream):
     global launch_count
     _check(lib().uvb_sp_signal(_c.cast(flag_ptrs, _vp), int(n), int(value) & 0xffffffff, stream))
+    launch_count += 1
+
+
+def sp_signal_wait(flag_ptrs, n, value, wait_ptr, stream):
+    global launch_count
+    _check(lib().uvb_sp_signal_wait(_c.cast(flag_ptrs, _vp), int(n), int(value) & 0xffffffff, int(wait_ptr), stream))
     launch_count += 1
 
 
