@@ -35,6 +35,7 @@ _FLAG_BYTES = 4096
 _O_FLAG_OFF = 128          # bytes: qkv flags at [0, 4p), o flags at [128, 128 + 4p), second-phase qkv flags at [256, ...)
 _QKV2_FLAG_OFF = 256
 _SIDE_CTAS = 16            # SMs the second-phase producers may take while the first attention launch runs
+PHASED_DEFAULT = False     # see UlyssesP2P.__init__
 _CONTEXTS = {}
 _DISABLED = None
 
@@ -143,8 +144,12 @@ class UlyssesP2P:
         self.o_flag_peers = _ext.ptr_array([pb + lay["o_flag_bytes"] for pb in self.peer_base])
         self.qkv2_flag_peers = _ext.ptr_array([pb + lay["qkv2_flag_bytes"] for pb in self.peer_base])
         # Phased exchange (attend_phased): the heads of every group are exchanged in two phases, the second one on a
-        # side stream under the first attention launch.  Off for head counts it cannot split.
-        self.phased = os.environ.get("UVB_SP_PHASED", "1") != "0" and self.n >= 2
+        # side stream under the first attention launch.  MEASURED AND REJECTED as a default (profiles/r02d, 2 GPUs:
+        # 14B 2443 vs 2507 TFLOP/s, 1.3B 2214 vs 2370): the second-phase producers re-read every q/k row on a
+        # handful of SMs for ~2 ms, and the attention CTA pairs that start late on those SMs still own a full share of
+        # the persistent kernel's static schedule, so the first attention launch ends that much later than the
+        # 1 ms of transfer it hides.  Kept as an opt-in (PHASED_DEFAULT / UVB_SP_PHASED=1) for the record.
+        self.phased = (os.environ.get("UVB_SP_PHASED", "1" if PHASED_DEFAULT else "0") != "0") and self.n >= 2
         self.side = torch.cuda.Stream(device=device) if self.phased else None
         self.send_sb, self.send_sl = lay["send_sb"], lay["send_sl"]      # element strides of a slot inside [B, p, s, n, 128]
         raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=device)
