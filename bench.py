@@ -395,17 +395,13 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
             elif ctx is not None:
                 # fused exchange: producers store into the peers' buffers, attention stores o into the owners'
                 ctx.next_epoch()
-
-                def produce(lo, hi, max_ctas, t=t):
-                    _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid,
-                                      tok_offset=rank * s, groups=world,
-                                      peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl),
-                                      head_range=(lo, hi), max_ctas=max_ctas)
-                    _ext.head_scatter(t["v"], world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl),
-                                      head_range=(lo, hi), max_ctas=max_ctas)
-
-                # marks: producers_phase_a, qkv_signal_wait, self_attention, [qkv_wait_phase_b, self_attention_phase_b,] o_signal_wait
-                ctx.attend_phased(produce, None, mark=mark)
+                _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid,
+                                  tok_offset=rank * s, groups=world,
+                                  peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
+                mark("prologue")
+                _ext.head_scatter(t["v"], world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
+                mark("head_scatter")
+                ctx.attend(None, mark=mark)          # marks: qkv_signal_wait, self_attention, o_signal_wait
             else:
                 q_send, k_send = _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs,
                                                    grid_sizes=grid, tok_offset=rank * s, groups=world)
@@ -464,8 +460,6 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
     heads_local = heads // world
     if "self_attention" in seg:
         a = sum(seg["self_attention"]) / len(seg["self_attention"])
-        if "self_attention_phase_b" in seg:       # phased exchange: two launches per layer
-            a += sum(seg["self_attention_phase_b"]) / len(seg["self_attention_phase_b"])
         fs_local = fs / world                                  # this rank's head shard
         achieved = fs_local / (a * 1e-3) * 1e-12
         res["roofline"] = {
@@ -601,7 +595,6 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
         torch.cuda.empty_cache()
     res["sharding"] = ("none" if world == 1 else (
         f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
-        + (", q/k/v in two head phases (second one under the first attention launch)" if ctx.phased else "")
         if ctx is not None else f"Ulysses heads/{world} over NCCL all-to-all"))
     res["geometry"] = {"video_tokens": L, "text_tokens": text_len, "dim": dim, "heads": heads, "layers": layers,
                        "l2_policy": f"inputs larger than L2: 4 rotating layer-input sets of {3 * s * dim * 2 / 1e6:.0f} MB each"}

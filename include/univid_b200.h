@@ -146,20 +146,15 @@ int uvb_sp_signal_wait(void* const* flag_ptrs, int n, uint32_t value, const void
 
 /* uvb_qk_norm_rope with peer stores: with n_peers = p > 0 (N == hpg * p) head group j of element (b, l) goes
  * to {q,k}_peers[j] + b*out_sb + l*out_sl + (n % hpg)*128 + d; {q,k}_peers are HOST arrays of p DEVICE
- * pointers, q_out/k_out/out_sg are ignored.  n_peers == 0 is uvb_qk_norm_rope.
- * Phased exchange: only heads whose index inside their group (n % hpg) lies in [head_lo, head_hi) are stored
- * (pass 0, hpg for all), and max_ctas > 0 caps the grid of the streaming kernel so that a phase issued on a side
- * stream leaves most SMs to the attention kernel it overlaps with (0 = whole device).  The same two arguments
- * exist on uvb_head_scatter_sp. */
+ * pointers, q_out/k_out/out_sg are ignored.  n_peers == 0 is uvb_qk_norm_rope. */
 int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const float* wq,
                         const float* wk, const float* cos_sin, const float* row_scale,
                         const float* pre_bias, void* q_out, void* k_out, void* const* q_peers,
                         void* const* k_peers, int n_peers, int B, int L, int N,
                         const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
-                        int64_t out_sl, int64_t out_sg, int head_lo, int head_hi, int max_ctas, void* stream);
+                        int64_t out_sl, int64_t out_sg, void* stream);
 int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n_peers, int B, int L,
-                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, int head_lo, int head_hi,
-                        int max_ctas, void* stream);
+                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream);
 /* uvb_fmha_fwd_bf16 on a head shard [B, Lq, N, 128] whose output rows [j*Lq/p, (j+1)*Lq/p) are stored into
  * rank j's buffer o_peers[j] = [B, Lq/p, total_heads, 128] at heads [head_offset, head_offset + N). */
 int uvb_fmha_fwd_sp_bf16(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,

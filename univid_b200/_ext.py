@@ -67,9 +67,9 @@ def lib():
     _u32, _pp = _c.c_uint32, _c.POINTER(_c.c_void_p)
     L.uvb_qk_norm_rope_sp.restype = _i
     L.uvb_qk_norm_rope_sp.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
-                                      _vp, _i, _f, _i, _i64, _i64, _i64, _i, _i, _i, _vp]
+                                      _vp, _i, _f, _i, _i64, _i64, _i64, _vp]
     L.uvb_head_scatter_sp.restype = _i
-    L.uvb_head_scatter_sp.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp]
+    L.uvb_head_scatter_sp.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp]
     L.uvb_sp_signal_wait.restype = _i
     L.uvb_sp_signal_wait.argtypes = [_vp, _i, _u32, _vp, _vp]
     L.uvb_fmha_fwd_sp_bf16.restype = _i
@@ -196,14 +196,11 @@ def ptr_array(ptrs):
 
 
 def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=None, tok_offset=0,
-                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None, peers=None, head_range=None,
-                 max_ctas=0):
+                 row_scale=None, pre_bias=None, groups=1, q_out=None, k_out=None, peers=None):
     """Fused RMSNorm (+RoPE) of q and/or k: [B, L, dim] -> bf16 [B, L, N, 128] (groups == 1) or the
     Ulysses send layout [groups, B, L, N/groups, 128].  See uvb_qk_norm_rope in the header.
     peers = (q_ptrs, k_ptrs, out_sb, out_sl): head group j is stored through q_ptrs[j] / k_ptrs[j]
-    (ctypes void*[groups] of peer-mapped device addresses, uvb_qk_norm_rope_sp) and nothing is returned.
-    head_range = (lo, hi): with peers, store only the heads lo <= n % (N/groups) < hi (one phase of the exchange);
-    max_ctas caps the grid of the streaming kernel (0 = whole device)."""
+    (ctypes void*[groups] of peer-mapped device addresses, uvb_qk_norm_rope_sp) and nothing is returned."""
     global launch_count
     ref = q_in if q_in is not None else k_in
     _require_cuda(q_in, k_in, wq, wk, cos_sin, row_scale, pre_bias)
@@ -235,8 +232,7 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
             _ptr(cos_sin), _ptr(row_scale), _ptr(pre_bias), None, None,
             None if q_in is None else _c.cast(q_ptrs, _vp), None if k_in is None else _c.cast(k_ptrs, _vp),
             groups, B, L, N, None if grid is None else _c.cast(grid, _vp), int(tok_offset), float(eps), hpg,
-            int(out_sb), int(out_sl), 0, 0 if head_range is None else int(head_range[0]),
-            hpg if head_range is None else int(head_range[1]), int(max_ctas), _stream(ref)))
+            int(out_sb), int(out_sl), 0, _stream(ref)))
         launch_count += 1
         return None, None
     q_out = _grouped_out(q_out, q_in, groups, B, L, hpg, ref.device)
@@ -260,10 +256,9 @@ def qk_norm_rope(q_in, k_in, wq, wk, eps, num_heads, cos_sin=None, grid_sizes=No
     return q_out, k_out
 
 
-def head_scatter(v, groups, out=None, peers=None, head_range=None, max_ctas=0):
+def head_scatter(v, groups, out=None, peers=None):
     """v [B, L, N, 128] bf16 -> [groups, B, L, N/groups, 128] (Ulysses send layout); with
-    peers = (ptrs, out_sb, out_sl) head group j is stored through ptrs[j] (uvb_head_scatter_sp); head_range /
-    max_ctas as in qk_norm_rope."""
+    peers = (ptrs, out_sb, out_sl) head group j is stored through ptrs[j] (uvb_head_scatter_sp)."""
     global launch_count
     _require_cuda(v)
     B, L, N, D = v.shape
@@ -273,8 +268,7 @@ def head_scatter(v, groups, out=None, peers=None, head_range=None, max_ctas=0):
     if peers is not None:
         ptrs, out_sb, out_sl = peers
         _check(lib().uvb_head_scatter_sp(_ptr(v), None, _c.cast(ptrs, _vp), groups, B, L, N, hpg, int(out_sb),
-                                         int(out_sl), 0, 0 if head_range is None else int(head_range[0]),
-                                         hpg if head_range is None else int(head_range[1]), int(max_ctas), _stream(v)))
+                                         int(out_sl), 0, _stream(v)))
         launch_count += 1
         return None
     out = _grouped_out(out, v, groups, B, L, hpg, v.device)

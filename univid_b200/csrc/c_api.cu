@@ -452,7 +452,7 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
 }
 
 template <typename InT, bool kPeers>
-int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream, int max_ctas) {
+int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
   const int dim = p.N * 128;
   const dim3 block(uvb::kNormRopeWarps * 32);
   // q and k together (self-attention): one warp group per token, both rows in flight (UVB_KNOB_PROLOGUE_PAIR = 0
@@ -466,8 +466,7 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream, int ma
     auto launch = [&](auto kern, int dyn_bytes, int rows_per_stage) -> int {
       UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes));
       const long long chunks = (static_cast<long long>(p.B) * p.L + rows_per_stage - 1) / rows_per_stage;
-      long long lim = max_ctas > 0 && max_ctas < sms ? max_ctas : sms;    // phased exchange: leave SMs to the attention
-      const unsigned grid = static_cast<unsigned>(chunks < lim ? chunks : lim);
+      const unsigned grid = static_cast<unsigned>(chunks < sms ? chunks : sms);
       kern<<<grid, uvb::kStreamThreads, dyn_bytes, stream>>>(p);
       UVB_CUDA(cudaGetLastError());
       return UVB_OK;
@@ -518,9 +517,8 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream, int ma
 }
 
 template <typename InT>
-int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream, int max_ctas) {
-  return p.n_peers > 0 ? launch_norm_rope_t<InT, true>(p, stream, max_ctas)
-                       : launch_norm_rope_t<InT, false>(p, stream, max_ctas);
+int launch_norm_rope(const uvb::NormRopeParams& p, cudaStream_t stream) {
+  return p.n_peers > 0 ? launch_norm_rope_t<InT, true>(p, stream) : launch_norm_rope_t<InT, false>(p, stream);
 }
 
 int linear_impl(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx, int64_t ldw,
@@ -600,7 +598,7 @@ int uvb_qk_norm_rope(const void* q_in, const void* k_in, int in_dtype, const flo
                      int64_t out_sl, int64_t out_sg, void* stream) {
   return uvb_qk_norm_rope_sp(q_in, k_in, in_dtype, wq, wk, cos_sin, row_scale, pre_bias, q_out, k_out,
                              nullptr, nullptr, 0, B, L, N, grid_fhw, tok_offset, eps, hpg, out_sb, out_sl,
-                             out_sg, 0, hpg, 0, stream);
+                             out_sg, stream);
 }
 
 int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const float* wq,
@@ -608,10 +606,8 @@ int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const 
                         const float* pre_bias, void* q_out, void* k_out, void* const* q_peers,
                         void* const* k_peers, int n_peers, int B, int L, int N,
                         const int32_t* grid_fhw, int tok_offset, float eps, int hpg, int64_t out_sb,
-                        int64_t out_sl, int64_t out_sg, int head_lo, int head_hi, int max_ctas, void* stream) {
+                        int64_t out_sl, int64_t out_sg, void* stream) {
   if (q_in == nullptr && k_in == nullptr) return fail(UVB_ERR_INVALID, "q_in and k_in are both null");
-  if (head_lo < 0 || head_hi > hpg || head_lo >= head_hi)
-    return fail(UVB_ERR_INVALID, "bad head range [%d, %d) for %d heads per group", head_lo, head_hi, hpg);
   if (n_peers < 0 || n_peers > uvb::kMaxPeers) return fail(UVB_ERR_INVALID, "n_peers=%d", n_peers);
   if (n_peers > 0) {
     if (hpg <= 0 || N != hpg * n_peers) return fail(UVB_ERR_INVALID, "N=%d != hpg=%d * n_peers=%d", N, hpg, n_peers);
@@ -664,8 +660,6 @@ int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const 
   p.out_sl = out_sl;
   p.out_sg = out_sg;
   p.n_peers = n_peers;
-  p.head_lo = head_lo;
-  p.head_hi = head_hi;
   for (int j = 0; j < n_peers; ++j) {
     p.q_peer[j] = q_in != nullptr ? static_cast<__nv_bfloat16*>(q_peers[j]) : nullptr;
     p.k_peer[j] = k_in != nullptr ? static_cast<__nv_bfloat16*>(k_peers[j]) : nullptr;
@@ -673,20 +667,17 @@ int uvb_qk_norm_rope_sp(const void* q_in, const void* k_in, int in_dtype, const 
       return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return in_dtype == UVB_BF16 ? launch_norm_rope<__nv_bfloat16>(p, st, max_ctas) : launch_norm_rope<float>(p, st, max_ctas);
+  return in_dtype == UVB_BF16 ? launch_norm_rope<__nv_bfloat16>(p, st) : launch_norm_rope<float>(p, st);
 }
 
 int uvb_head_scatter_bf16(const void* v_in, void* v_out, int B, int L, int N, int hpg,
                           int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream) {
-  return uvb_head_scatter_sp(v_in, v_out, nullptr, 0, B, L, N, hpg, out_sb, out_sl, out_sg, 0, hpg, 0, stream);
+  return uvb_head_scatter_sp(v_in, v_out, nullptr, 0, B, L, N, hpg, out_sb, out_sl, out_sg, stream);
 }
 
 int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n_peers, int B, int L,
-                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, int head_lo, int head_hi,
-                        int max_ctas, void* stream) {
+                        int N, int hpg, int64_t out_sb, int64_t out_sl, int64_t out_sg, void* stream) {
   if (v_in == nullptr || (v_out == nullptr && n_peers == 0)) return fail(UVB_ERR_INVALID, "null pointer");
-  if (hpg > 0 && (head_lo < 0 || head_hi > hpg || head_lo >= head_hi))
-    return fail(UVB_ERR_INVALID, "bad head range [%d, %d) for %d heads per group", head_lo, head_hi, hpg);
   if (B <= 0 || L <= 0 || N <= 0 || hpg <= 0 || N % hpg != 0)
     return fail(UVB_ERR_INVALID, "bad shape B=%d L=%d N=%d hpg=%d", B, L, N, hpg);
   if (n_peers < 0 || n_peers > uvb::kMaxPeers || (n_peers > 0 && (peers == nullptr || N != hpg * n_peers)))
@@ -704,8 +695,6 @@ int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n
   p.out_sl = out_sl;
   p.out_sg = out_sg;
   p.n_peers = n_peers;
-  p.head_lo = head_lo;
-  p.head_hi = head_hi;
   for (int j = 0; j < n_peers; ++j) {
     if (peers[j] == nullptr) return fail(UVB_ERR_INVALID, "null peer pointer %d", j);
     p.peer[j] = static_cast<__nv_bfloat16*>(peers[j]);
@@ -713,7 +702,6 @@ int uvb_head_scatter_sp(const void* v_in, void* v_out, void* const* peers, int n
   const long long total = static_cast<long long>(B) * L * N * 16;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  if (max_ctas > 0 && blocks > 8LL * max_ctas) blocks = 8LL * max_ctas;    // 8 CTAs of 256 threads fill one SM
   uvb::head_scatter_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   UVB_CUDA(cudaGetLastError());
   return UVB_OK;

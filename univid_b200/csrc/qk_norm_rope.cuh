@@ -41,9 +41,6 @@ struct NormRopeParams {
   int n_peers;
   __nv_bfloat16* q_peer[kMaxPeers];
   __nv_bfloat16* k_peer[kMaxPeers];
-  // Phased exchange: only the heads whose index INSIDE their group, n % hpg, lies in [head_lo, head_hi) are stored
-  // (the whole row is still read: the norm runs over the full width).  Default [0, hpg).
-  int head_lo, head_hi;
 };
 
 template <typename InT>
@@ -115,7 +112,7 @@ __device__ __forceinline__ void norm_rope_row(RowVec<InT> (&v)[VPL], const float
                                               long long out_sg, int dim, float eps, bool rotate,
                                               const float (&cs)[8], float rscale,
                                               const float* __restrict__ pre_bias, int lane,
-                                              float* red, int bar_id, int head_lo = 0, int head_hi = 1 << 30) {
+                                              float* red, int bar_id) {
   constexpr int kStride = 32 * WPR;
 
   auto fetch = [&](int i, float* x) {
@@ -161,10 +158,6 @@ __device__ __forceinline__ void norm_rope_row(RowVec<InT> (&v)[VPL], const float
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vec = lane + kStride * i;
-    {
-      const int hg = (vec >> 4) % hpg;
-      if (hg < head_lo || hg >= head_hi) continue;     // not part of this exchange phase
-    }
     float y[8];
     fetch(i, y);
     if (normed) {
@@ -222,8 +215,7 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
                                                       int hpg, long long out_sg, int dim, float eps,
                                                       bool rotate, const float (&cs)[8],
                                                       float rscale,
-                                                      const float* __restrict__ pre_bias, int lane,
-                                                      int head_lo = 0, int head_hi = 1 << 30) {
+                                                      const float* __restrict__ pre_bias, int lane) {
   const int nvec = dim / 8;
   float ss = 0.f;
   for (int vec = lane; vec < nvec; vec += 32) {
@@ -248,10 +240,6 @@ __device__ __forceinline__ void norm_rope_row_generic(const InT* __restrict__ in
   const bool normed = w != nullptr;
   const float rinv = normed ? rsqrtf(ss / static_cast<float>(dim) + eps) : 1.0f;
   for (int vec = lane; vec < nvec; vec += 32) {
-    {
-      const int hg = (vec >> 4) % hpg;
-      if (hg < head_lo || hg >= head_hi) continue;
-    }
     RowVec<InT> v;
     v.load(in + vec * 8);
     float x[8];
@@ -349,16 +337,14 @@ qk_norm_rope_kernel(const __grid_constant__ NormRopeParams p) {
     load_row<InT, VPL, WPR>(v, src + in_off, lane);
     if (pre_bias != nullptr) {
       norm_rope_row<InT, VPL, WPR, true>(v, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
-                                         rotate, cs, rscale, pre_bias, lane, red + group * WPR, 1 + group,
-                                         p.head_lo, p.head_hi);
+                                         rotate, cs, rscale, pre_bias, lane, red + group * WPR, 1 + group);
     } else {
       norm_rope_row<InT, VPL, WPR, false>(v, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps,
-                                          rotate, cs, rscale, nullptr, lane, red + group * WPR, 1 + group,
-                                          p.head_lo, p.head_hi);
+                                          rotate, cs, rscale, nullptr, lane, red + group * WPR, 1 + group);
     }
   } else {
     norm_rope_row_generic<InT>(src + in_off, w, dst, peers, out_off, p.hpg, p.out_sg, dim, p.eps, rotate, cs,
-                               rscale, pre_bias, lane, p.head_lo, p.head_hi);
+                               rscale, pre_bias, lane);
   }
 }
 
@@ -410,10 +396,10 @@ qk_norm_rope_pair_kernel(const __grid_constant__ NormRopeParams p) {
   const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
   norm_rope_row<InT, VPL, WPR, false>(vq, p.wq, p.q_out + out_off, kPeers ? p.q_peer : nullptr, out_off, p.hpg,
                                       p.out_sg, dim, p.eps, rotate, cs, 1.0f, nullptr, lane, red[0] + group * WPR,
-                                      1 + group, p.head_lo, p.head_hi);
+                                      1 + group);
   norm_rope_row<InT, VPL, WPR, false>(vk, p.wk, p.k_out + out_off, kPeers ? p.k_peer : nullptr, out_off, p.hpg,
                                       p.out_sg, dim, p.eps, rotate, cs, 1.0f, nullptr, lane, red[1] + group * WPR,
-                                      1 + group, p.head_lo, p.head_hi);
+                                      1 + group);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -457,24 +443,13 @@ struct StreamSmem {
   static constexpr int kDynBytes = kBarOff + 2 * kStages * 8 + 2 * kStreamConsumerWarps * 4 + 128;
 };
 
-// Per-lane store plan of the streaming kernel, computed ONCE per CTA: lane l always owns the same 16-byte vectors
-// (l + 32 WPR i) of every row, so the head-group split (n / hpg, n % hpg: integer divisions by a runtime value), the
-// offset inside the destination row and the phase predicate are loop invariants.  (Round-2 SASS of the first
-// version: ~850 instructions per row, most of them these divisions repeated per vector and row.)
-template <int VPL>
-struct StorePlan {
-  int grp[VPL];        // head group n / hpg (destination rank)
-  int off[VPL];        // (n % hpg) * 128 + d0: element offset inside the group's row
-  unsigned active;     // bit i: vector i belongs to this exchange phase
-};
-
 // one row (already in shared memory) -> normalised, rotated, bf16, stored
 template <int VPL, int WPR, bool kPeers>
 __device__ __forceinline__ void stream_row(const uint8_t* __restrict__ srow, const float* __restrict__ w_s,
-                                           bool normed, __nv_bfloat16* __restrict__ out_base,
-                                           __nv_bfloat16* const* peers, long long out_off, long long out_sg,
+                                           bool normed, __nv_bfloat16* __restrict__ out_row,
+                                           __nv_bfloat16* const* peers, long long out_off, int hpg, long long out_sg,
                                            float eps, bool rotate, const float (&cs)[8], int lane, float* red,
-                                           int bar_id, const StorePlan<VPL>& plan) {
+                                           int bar_id) {
   constexpr int kStride = 32 * WPR;
   constexpr int kDim = 256 * VPL * WPR;
   float x[VPL][8];
@@ -500,9 +475,9 @@ __device__ __forceinline__ void stream_row(const uint8_t* __restrict__ srow, con
     for (int i = 0; i < WPR; ++i) ss += red[i];
   }
   const float rinv = normed ? rsqrtf(ss / static_cast<float>(kDim) + eps) : 1.0f;
+  const bool flat = hpg * 128 == kDim && !kPeers;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    if (((plan.active >> i) & 1u) == 0u) continue;       // not part of this exchange phase
     const int vec = lane + kStride * i;
     float y[8];
 #pragma unroll
@@ -535,33 +510,20 @@ __device__ __forceinline__ void stream_row(const uint8_t* __restrict__ srow, con
       o[pr] = pack_bf16x2(a, b);
     }
     __nv_bfloat16* dst;
-    if constexpr (kPeers) {
-      dst = peers[plan.grp[i]] + out_off + plan.off[i];           // rank grp's buffer, over NVLink
+    if (flat) {
+      dst = out_row + vec * 8;
     } else {
-      dst = out_base + out_off + static_cast<long long>(plan.grp[i]) * out_sg + plan.off[i];
+      const int n = vec >> 4;
+      const int d0 = (vec & 15) * 8;
+      if constexpr (kPeers) {
+        dst = peers[n / hpg] + out_off + (n % hpg) * 128 + d0;
+      } else {
+        dst = out_row + static_cast<long long>(n / hpg) * out_sg + (n % hpg) * 128 + d0;
+      }
     }
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o[0]),
                  "r"(o[1]), "r"(o[2]), "r"(o[3])
                  : "memory");
-  }
-}
-
-// floor(a / d) and a % d for 0 <= a < 2^23 through one fp32 multiply and a fix-up (exact: |error| of the product
-// is below 1 at this range); plain integer division otherwise
-__device__ __forceinline__ void fast_divmod(int a, int d, float inv_d, bool small, int& q, int& r) {
-  if (small) {
-    q = __float2int_rz(__int2float_rn(a) * inv_d);
-    r = a - q * d;
-    if (r >= d) {
-      ++q;
-      r -= d;
-    } else if (r < 0) {
-      --q;
-      r += d;
-    }
-  } else {
-    q = a / d;
-    r = a - q * d;
   }
 }
 
@@ -577,7 +539,7 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
   float* w_s = reinterpret_cast<float*>(smem + SM::kWOff);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
   uint64_t* empty = full + kStages;
-  float* red = reinterpret_cast<float*>(empty + kStages);      // [2][kStreamConsumerWarps]
+  float* red = reinterpret_cast<float*>(empty + kStages);      // [2][8]
   const int warp = threadIdx.x >> 5;
   const long long rows = static_cast<long long>(p.B) * p.L;
   const long long n_chunks = (rows + kRows - 1) / kRows;
@@ -620,31 +582,14 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
     const int group = warp / WPR;                              // token inside the stage
     const int lane = threadIdx.x - group * (32 * WPR);
     const bool normed_q = p.wq != nullptr, normed_k = p.wk != nullptr;
-    // loop invariants: where this lane's vectors go, the RoPE pair indices, the grid of sample 0
-    StorePlan<VPL> plan;
-    plan.active = 0u;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vec = lane + 32 * WPR * i;
-      const int n = vec >> 4;
-      plan.grp[i] = n / p.hpg;
-      const int hg = n - plan.grp[i] * p.hpg;
-      plan.off[i] = hg * 128 + (vec & 15) * 8;
-      if (hg >= p.head_lo && hg < p.head_hi) plan.active |= 1u << i;
-    }
-    const int jj0 = 4 * (lane & 15);
-    const bool small = rows + p.tok_offset < (1LL << 23);
     int it = 0;
     for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
       const int slot = it % kStages;
       const long long row = c * kRows + group;
       mbar_wait(&full[slot], (it / kStages) & 1);
       if (row < rows) {
-        int b = 0, l = static_cast<int>(row);
-        if (p.B > 1) {
-          b = static_cast<int>(row / p.L);
-          l = static_cast<int>(row - static_cast<long long>(b) * p.L);
-        }
+        const int b = p.B == 1 ? 0 : static_cast<int>(row / p.L);
+        const int l = static_cast<int>(row - static_cast<long long>(b) * p.L);
         float cs[8];
         bool rotate = false;
         if (p.cos_sin != nullptr) {
@@ -653,12 +598,10 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
           const int tok = p.tok_offset + l;
           rotate = tok < p.grid[gb][0] * gh * gw;
           if (rotate) {
-            int t2, pw, pf, ph;
-            fast_divmod(tok, gw, 1.0f / static_cast<float>(gw), small, t2, pw);     // t2 = tok / gw
-            fast_divmod(t2, gh, 1.0f / static_cast<float>(gh), small, pf, ph);      // pf = tok / (gh gw), ph = t2 % gh
+            const int pf = tok / (gh * gw), ph = (tok / gw) % gh, pw = tok % gw;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int jj = jj0 + i;
+              const int jj = 4 * (lane & 15) + i;
               const int pos = jj < 22 ? pf : (jj < 43 ? ph : pw);
               const float2 v = __ldg(p.cos_sin + pos * 64 + jj);
               cs[2 * i] = v.x;
@@ -673,10 +616,11 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
         const long long out_off = static_cast<long long>(b) * p.out_sb + static_cast<long long>(l) * p.out_sl;
         const uint8_t* sq = smem + slot * SM::kStageBytes + group * SM::kRowBytes;
         const uint8_t* sk = sq + kRows * SM::kRowBytes;
-        stream_row<VPL, WPR, kPeers>(sq, w_s, normed_q, p.q_out, p.q_peer, out_off, p.out_sg, p.eps, rotate, cs, lane,
-                                     red + group * WPR, 1 + group, plan);
-        stream_row<VPL, WPR, kPeers>(sk, w_s + SM::kDim, normed_k, p.k_out, p.k_peer, out_off, p.out_sg, p.eps, rotate,
-                                     cs, lane, red + kStreamConsumerWarps + group * WPR, 1 + group, plan);
+        stream_row<VPL, WPR, kPeers>(sq, w_s, normed_q, p.q_out + out_off, p.q_peer, out_off, p.hpg, p.out_sg, p.eps,
+                                     rotate, cs, lane, red + group * WPR, 1 + group);
+        stream_row<VPL, WPR, kPeers>(sk, w_s + SM::kDim, normed_k, p.k_out + out_off, p.k_peer, out_off, p.hpg,
+                                     p.out_sg, p.eps, rotate, cs, lane, red + kStreamConsumerWarps + group * WPR,
+                                     1 + group);
       }
       // both rows of this warp's token have been read out of the stage
       __syncwarp();
@@ -693,7 +637,6 @@ struct HeadScatterParams {
   long long out_sb, out_sl, out_sg;
   int n_peers;                              // > 0: group j goes through peer[j] (see NormRopeParams)
   __nv_bfloat16* peer[kMaxPeers];
-  int head_lo, head_hi;                     // heads (index inside the group) copied by this launch
 };
 
 __global__ void __launch_bounds__(256) head_scatter_kernel(const __grid_constant__ HeadScatterParams p) {
@@ -705,7 +648,6 @@ __global__ void __launch_bounds__(256) head_scatter_kernel(const __grid_constant
     const int vec = static_cast<int>(i % nvec_row);
     const int b = static_cast<int>(row / p.L), l = static_cast<int>(row % p.L);
     const int n = vec >> 4, d0 = (vec & 15) * 8;
-    if (n % p.hpg < p.head_lo || n % p.hpg >= p.head_hi) continue;
     const uint4 val = __ldg(reinterpret_cast<const uint4*>(p.in) + i);
     __nv_bfloat16* base = p.n_peers > 0 ? p.peer[n / p.hpg]
                                         : p.out + static_cast<long long>(n / p.hpg) * p.out_sg;
@@ -733,7 +675,11 @@ __global__ void sp_signal_kernel(const __grid_constant__ SpSignalParams p) {
   }
 }
 
-// Waits like sp_wait_kernel below after publishing like sp_signal_kernel (one launch instead of two).
+// Spins until *f >= value (wrap-safe).  A rank may legitimately be seconds or minutes late (rank-0-only VAE decode or
+// save, offload_model reloads, lazy initialisation, a profiler pause), so the bound is generous and configurable like
+// a collective's watchdog: timeout_ns = 0 waits for ever; otherwise the kernel traps (reported by the host as a launch
+// failure) after that much wall time (%globaltimer) without the flag arriving.  Default 600 s
+// (UVB_KNOB_SP_WAIT_TIMEOUT_S), the default torch.distributed gives an NCCL collective.
 __device__ __forceinline__ void sp_wait_flag(const uint32_t* f, uint32_t value, unsigned long long timeout_ns) {
   if (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
     const unsigned long long t0 = globaltimer_ns();
@@ -746,6 +692,13 @@ __device__ __forceinline__ void sp_wait_flag(const uint32_t* f, uint32_t value, 
   }
 }
 
+__global__ void sp_wait_kernel(const uint32_t* flags, int n, uint32_t value, unsigned long long timeout_ns) {
+  if (threadIdx.x < n) sp_wait_flag(flags + threadIdx.x, value, timeout_ns);
+  __syncthreads();
+  __threadfence_system();
+}
+
+// sp_signal_kernel followed by sp_wait_kernel in ONE launch (the exchange needs the pair twice per layer)
 __global__ void sp_signal_wait_kernel(const __grid_constant__ SpSignalParams p, const uint32_t* flags,
                                       unsigned long long timeout_ns) {
   if (threadIdx.x < p.n) {
@@ -753,17 +706,6 @@ __global__ void sp_signal_wait_kernel(const __grid_constant__ SpSignalParams p, 
     st_release_sys(p.flag[threadIdx.x], p.value);
     sp_wait_flag(flags + threadIdx.x, p.value, timeout_ns);
   }
-  __syncthreads();
-  __threadfence_system();
-}
-
-// Spins until every flags[i] >= value (wrap-safe).  A rank may legitimately be seconds or minutes late (rank-0-only
-// VAE decode or save, offload_model reloads, lazy initialisation, a profiler pause), so the bound is generous and
-// configurable like a collective's watchdog: timeout_ns = 0 waits for ever; otherwise the kernel traps (reported by
-// the host as a launch failure) after that much wall time (%globaltimer) without the flag arriving.  Default 600 s
-// (UVB_KNOB_SP_WAIT_TIMEOUT_S), the default torch.distributed gives an NCCL collective.
-__global__ void sp_wait_kernel(const uint32_t* flags, int n, uint32_t value, unsigned long long timeout_ns) {
-  if (threadIdx.x < n) sp_wait_flag(flags + threadIdx.x, value, timeout_ns);
   __syncthreads();
   __threadfence_system();
 }

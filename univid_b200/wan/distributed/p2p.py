@@ -32,10 +32,7 @@ import torch.distributed as dist
 from ... import _ext
 
 _FLAG_BYTES = 4096
-_O_FLAG_OFF = 128          # bytes: qkv flags at [0, 4p), o flags at [128, 128 + 4p), second-phase qkv flags at [256, ...)
-_QKV2_FLAG_OFF = 256
-_SIDE_CTAS = 16            # SMs the second-phase producers may take while the first attention launch runs
-PHASED_DEFAULT = False     # see UlyssesP2P.__init__
+_O_FLAG_OFF = 128          # bytes: qkv flags at [0, 4p), o flags at [128, 128 + 4p)
 _CONTEXTS = {}
 _DISABLED = None
 
@@ -70,8 +67,7 @@ def exchange_layout(B, s, N, p, rank):
     return dict(n=n, elems=elems, off_q=off_q, off_k=off_k, off_v=off_v, off_o=off_o,
                 nbytes=off_o + _align(elems * 2), slot_bytes=rank * s * n * 128 * 2,
                 send_sb=p * s * n * 128, send_sl=n * 128, o_head_offset=rank * n,
-                qkv_flag_bytes=4 * rank, o_flag_bytes=_O_FLAG_OFF + 4 * rank,
-                qkv2_flag_bytes=_QKV2_FLAG_OFF + 4 * rank)
+                qkv_flag_bytes=4 * rank, o_flag_bytes=_O_FLAG_OFF + 4 * rank)
 
 
 class PeerExchangeUnavailable(RuntimeError):
@@ -142,15 +138,6 @@ class UlyssesP2P:
         self.o_peers = _ext.ptr_array([pb + self.off_o for pb in self.peer_base])
         self.qkv_flag_peers = _ext.ptr_array([pb + lay["qkv_flag_bytes"] for pb in self.peer_base])
         self.o_flag_peers = _ext.ptr_array([pb + lay["o_flag_bytes"] for pb in self.peer_base])
-        self.qkv2_flag_peers = _ext.ptr_array([pb + lay["qkv2_flag_bytes"] for pb in self.peer_base])
-        # Phased exchange (attend_phased): the heads of every group are exchanged in two phases, the second one on a
-        # side stream under the first attention launch.  MEASURED AND REJECTED as a default (profiles/r02d, 2 GPUs:
-        # 14B 2443 vs 2507 TFLOP/s, 1.3B 2214 vs 2370): the second-phase producers re-read every q/k row on a
-        # handful of SMs for ~2 ms, and the attention CTA pairs that start late on those SMs still own a full share of
-        # the persistent kernel's static schedule, so the first attention launch ends that much later than the
-        # 1 ms of transfer it hides.  Kept as an opt-in (PHASED_DEFAULT / UVB_SP_PHASED=1) for the record.
-        self.phased = (os.environ.get("UVB_SP_PHASED", "1" if PHASED_DEFAULT else "0") != "0") and self.n >= 2
-        self.side = torch.cuda.Stream(device=device) if self.phased else None
         self.send_sb, self.send_sl = lay["send_sb"], lay["send_sl"]      # element strides of a slot inside [B, p, s, n, 128]
         raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=device)
         self._raw = raw
@@ -186,50 +173,6 @@ class UlyssesP2P:
         if mark is not None:
             mark("self_attention")
         self.o_ready(stream)
-        if mark is not None:
-            mark("o_signal_wait")
-        return self.o_local
-
-    def attend_phased(self, produce, k_lens=None, mark=None):
-        """The whole exchange + attention with the q/k/v transfer hidden under compute.
-        produce(lo, hi, max_ctas) launches, on the CURRENT stream, the producer kernels that store the heads
-        lo <= h < hi of every head group into the peers (prologue with peer stores, v scatter); pass (0, n, 0)
-        semantics for a single phase.  Phase A = heads [0, hA) on the current stream with the whole device; phase B =
-        heads [hA, n) on a side stream with at most _SIDE_CTAS SMs, started right after phase A's producers, so its
-        NVLink transfer runs under the attention launch over phase A's heads; the second attention launch (phase B's
-        heads) waits for phase B's flags.  Output tiles go to the owners' o_recv as in attend().  Returns o_recv."""
-        if not self.phased:
-            produce(0, self.n, 0)
-            return self.attend(k_lens, mark)
-        n, r, world = self.n, self.rank, self.world
-        h_a = (n + 1) // 2
-        main = torch.cuda.current_stream(self.device)
-        ms = main.cuda_stream
-        produce(0, h_a, 0)
-        if mark is not None:
-            mark("producers_phase_a")
-        ev_a = main.record_event()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ev_a)          # phase B would only compete with phase A for NVLink
-            produce(h_a, n, _SIDE_CTAS)
-            _ext.sp_signal(self.qkv2_flag_peers, world, self.epoch, self.side.cuda_stream)
-            ev_b = self.side.record_event()
-        self.qkv_ready(ms)
-        if mark is not None:
-            mark("qkv_signal_wait")
-        _ext.fmha_fwd_sp(self.q_local[:, :, :h_a], self.k_local[:, :, :h_a], self.v_local[:, :, :h_a], self.o_peers,
-                         world, r * n, self.N, k_lens=k_lens)
-        if mark is not None:
-            mark("self_attention")
-        main.wait_event(ev_b)                   # this rank's phase-B producers are done (their inputs may be freed)
-        _ext.sp_wait(self.base + _QKV2_FLAG_OFF, world, self.epoch, ms)
-        if mark is not None:
-            mark("qkv_wait_phase_b")
-        _ext.fmha_fwd_sp(self.q_local[:, :, h_a:], self.k_local[:, :, h_a:], self.v_local[:, :, h_a:], self.o_peers,
-                         world, r * n + h_a, self.N, k_lens=k_lens)
-        if mark is not None:
-            mark("self_attention_phase_b")
-        self.o_ready(ms)
         if mark is not None:
             mark("o_signal_wait")
         return self.o_local

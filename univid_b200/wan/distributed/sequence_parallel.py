@@ -98,22 +98,13 @@ def sp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16):
         ctx.next_epoch()
         # v: the projection's epilogue TMA-stores every head group into its rank's exchange buffer (B == 1); q and k
         # go through the fused norm + RoPE prologue, which stores the same way
-        v = None
         if not _lin_to_peers(self.v, x, (ctx.v_peers, world, ctx.send_sl)):
             v = _lin(self.v, x).view(b, s, n, d)
-            v = (v if v.dtype == torch.bfloat16 else v.to(torch.bfloat16)).contiguous()
-        q_lin, k_lin, cs = _lin(self.q, x), _lin(self.k, x), _cos_sin_table(freqs, x.device)
-
-        def produce(lo, hi, max_ctas):
-            # heads [lo, hi) of every head group -> the peers (one phase of the exchange; ctx.attend_phased)
-            self._prologue(q_lin, k_lin, cs, grid_sizes, tok_offset=rank * s, groups=world,
-                           peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl), head_range=(lo, hi),
-                           max_ctas=max_ctas)
-            if v is not None:
-                _ext.head_scatter(v, world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl), head_range=(lo, hi),
-                                  max_ctas=max_ctas)
-
-        return self._out_proj(ctx.attend_phased(produce, _k_lens_arg(seq_lens, b, world * s, x.device)))
+            v = v if v.dtype == torch.bfloat16 else v.to(torch.bfloat16)
+            _ext.head_scatter(v.contiguous(), world, peers=(ctx.v_peers, ctx.send_sb, ctx.send_sl))
+        self._prologue(_lin(self.q, x), _lin(self.k, x), _cos_sin_table(freqs, x.device), grid_sizes, tok_offset=rank * s,
+                       groups=world, peers=(ctx.q_peers, ctx.k_peers, ctx.send_sb, ctx.send_sl))
+        return self._out_proj(ctx.attend(_k_lens_arg(seq_lens, b, world * s, x.device)))
     v = _lin(self.v, x).view(b, s, n, d)
     if v.dtype != torch.bfloat16:
         v = v.to(torch.bfloat16)

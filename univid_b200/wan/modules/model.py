@@ -255,8 +255,7 @@ class WanSelfAttention(_DropOperandsOnApply, nn.Module):
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
 
-    def _prologue(self, q_lin, k_lin, cos_sin, grid_sizes, tok_offset=0, groups=1, peers=None, head_range=None,
-                  max_ctas=0):
+    def _prologue(self, q_lin, k_lin, cos_sin, grid_sizes, tok_offset=0, groups=1, peers=None):
         """norm_q/norm_k (+RoPE) -> bf16 [B, L, N, 128] (or the Ulysses send layout when groups > 1; with
         `peers` the head groups are stored straight into the peer ranks' exchange buffers)."""
         wq, eps_q, pre_q = _norm_weight(self.norm_q)
@@ -269,8 +268,7 @@ class WanSelfAttention(_DropOperandsOnApply, nn.Module):
         k_lin = None if k_lin is None else _proj_for_kernel(k_lin)
         eps = eps_q if wq is not None else eps_k
         return _ext.qk_norm_rope(q_lin, k_lin, wq, wk, eps, self.num_heads, cos_sin=cos_sin,
-                                 grid_sizes=grid_sizes, tok_offset=tok_offset, groups=groups, peers=peers,
-                                 head_range=head_range, max_ctas=max_ctas)
+                                 grid_sizes=grid_sizes, tok_offset=tok_offset, groups=groups, peers=peers)
 
     def _out_proj(self, x):
         """o(x.flatten(2)); outside autocast the bf16 attention result is cast to the weight dtype
