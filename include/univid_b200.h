@@ -54,7 +54,8 @@ enum uvb_knob {
   UVB_KNOB_FMHA_POLY = 6,     /* lab builds only: one exp2 pair in every n (2, 3, 4) on the FMA pipe; 0 (default, shipped) = MUFU only */
   UVB_KNOB_SP_WAIT_TIMEOUT_S = 7, /* seconds uvb_sp_wait spins for a peer's hand-off flag before it traps (default 600,
                                      like an NCCL collective under torch.distributed); 0 = wait for ever */
-  UVB_KNOB_COUNT = 8
+  UVB_KNOB_XATTN_PAIR = 8,    /* 1: CTA-pair variant of the short-key (Lk <= 2048, cross-attention) kernel (default); 0: single CTAs */
+  UVB_KNOB_COUNT = 9
 };
 int uvb_set_knob(int knob, int value);
 int uvb_get_knob(int knob);

@@ -162,7 +162,10 @@ def attention_varlen(q, k, v, k_lens=None, softmax_scale=None, compute_dtype=tor
         p = p * key_pv_weight.float().view(1, 1, 1, lk)
     out = torch.matmul(p, vf).transpose(1, 2)                          # [B, Lq, N, D]
     if out_bias is not None:
-        out = out + out_bias.float().view(1, 1, n, d)
+        # the bias stands for sum_j p_j b = b * sum_j p_j: a row without any key (k_len == 0) gets none
+        has_keys = (p.sum(dim=-1) > 0).transpose(1, 2).unsqueeze(-1).float() if key_pv_weight is None else \
+            (torch.nan_to_num(torch.softmax(logits, dim=-1), nan=0.0).sum(dim=-1) > 0).transpose(1, 2).unsqueeze(-1).float()
+        out = out + out_bias.float().view(1, 1, n, d) * has_keys
     return out.to(compute_dtype).to(out_dtype)
 
 

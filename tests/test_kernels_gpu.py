@@ -184,6 +184,34 @@ def test_fmha_cta_pair_kernel(ext, b, lq, lk, n, lens):
     assert (got.float() - single.float()).abs().max().item() <= 4e-3
 
 
+@pytest.mark.parametrize("b,lq,lk,n,lens", [(1, 1950, 512, 12, None), (2, 700, 257, 3, [257, 40]), (1, 513, 2048, 2, None),
+                                             (1, 100, 77, 1, None), (3, 129, 513, 1, [513, 0, 1])])
+def test_short_key_kernel_single_cta_and_cta_pair_variants(ext, b, lq, lk, n, lens):
+    """Lk <= 2048 (cross-attention) runs the query-block-pipelined kernel; by default as CTA pairs (two Q/O buffers,
+    half-size K/V stages, shared-memory P panel), with uvb_set_knob(xattn_pair, 0) as single CTAs.  Both against the
+    oracle, with and without the per-key modifiers of the fused text weighting."""
+    g = torch.Generator().manual_seed(lq + 31 * lk)
+    q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+    kl = None if lens is None else torch.tensor(lens, dtype=torch.int32)
+    klc = None if kl is None else kl.cuda()
+    w = torch.ones(lk)
+    w[:lk // 4] = 1.25
+    bias = 0.1 * torch.randn(n * 128, generator=g)
+    want = orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32)
+    want_mod = orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32, key_pv_weight=w, out_bias=bias)
+    outs = {}
+    for mode in (1, 0):
+        old = ext.set_knob("xattn_pair", mode)
+        try:
+            outs[mode] = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=klc)
+            got_mod = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=klc, key_pv_weight=w.cuda(), out_bias=bias.cuda())
+        finally:
+            ext.set_knob("xattn_pair", old)
+        _check_attn(outs[mode], want)
+        _check_attn(got_mod, want_mod)
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 4e-3
+
+
 def test_fmha_peaked_logits_exercise_the_lazy_rescale(ext):
     """Row maxima that grow by far more than 2^8 from one key tile to the next force the in-place
     rescale of the TMEM accumulator."""

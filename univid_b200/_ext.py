@@ -21,7 +21,7 @@ EXPORTS = (
 )
 ABI_VERSION = 109
 KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
-         "fmha_poly": 6, "sp_wait_timeout_s": 7}
+         "fmha_poly": 6, "sp_wait_timeout_s": 7, "xattn_pair": 8}
 
 UVB_BF16, UVB_F32 = 0, 1
 _c = ctypes

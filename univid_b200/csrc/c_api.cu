@@ -63,6 +63,7 @@ int g_knobs[UVB_KNOB_COUNT] = {
     /* UVB_KNOB_PROLOGUE_PAIR */ 2,   // q and k both given: 2 streaming kernel (bulk-copy ring), 1 token-pair kernel, 0 row kernel
     /* UVB_KNOB_FMHA_POLY     */ 0,   // CTA-pair attention kernel: 1 exp2 pair in every n on the FMA pipe (0, 2, 3, 4)
     /* UVB_KNOB_SP_WAIT_TIMEOUT_S */ 600,   // seconds a rank waits for a peer's hand-off flag before trapping; 0 = for ever
+    /* UVB_KNOB_XATTN_PAIR    */ 1,   // CTA-pair variant of the short-key (cross-attention) kernel
 };
 
 int check_device() {
@@ -273,19 +274,18 @@ constexpr int pair_stages() { return kEarlyS ? 6 : 8; }
 
 // CTA pairs of the attention kernel the device can hold at once (one per TPC); also sets the kernel's
 // shared-memory attribute for the current device.  0 pairs = fall back to single CTAs.
-template <bool kEarlyS>
-int fmha_pair_workers(int sms, int* out) {
+template <auto kKernel, int kDynBytes>
+int pair_workers_of(int sms, int* out) {
   static int cached_dev = -1, cached = 0;
   int dev = 0;
   UVB_CUDA(cudaGetDevice(&dev));
   if (dev != cached_dev) {
-    using SM = uvb::FmhaSmem<pair_stages<kEarlyS>(), 1, 2, kEarlyS>;
-    auto kern = uvb::fmha_fwd_kernel<pair_stages<kEarlyS>(), 1, 2, false, kEarlyS>;
-    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynBytes));
+    auto kern = kKernel;
+    UVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynBytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(uvb::kFmhaThreads);
-    cfg.dynamicSmemBytes = SM::kDynBytes;
+    cfg.dynamicSmemBytes = kDynBytes;
     cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -302,6 +302,20 @@ int fmha_pair_workers(int sms, int* out) {
   }
   *out = cached;
   return UVB_OK;
+}
+
+template <bool kEarlyS>
+int fmha_pair_workers(int sms, int* out) {
+  return pair_workers_of<uvb::fmha_fwd_kernel<pair_stages<kEarlyS>(), 1, 2, false, kEarlyS>,
+                         uvb::FmhaSmem<pair_stages<kEarlyS>(), 1, 2, kEarlyS>::kDynBytes>(sms, out);
+}
+
+// short-key (cross-attention) variant as CTA pairs: two Q/O buffers, four 16 KiB K/V stages, P panels
+constexpr int kShortPairStages = 4;
+template <bool kKeyMod>
+int xattn_pair_workers(int sms, int* out) {
+  return pair_workers_of<uvb::fmha_fwd_kernel<kShortPairStages, 2, 2, kKeyMod>,
+                         uvb::FmhaSmem<kShortPairStages, 2, 2>::kDynBytes>(sms, out);
 }
 
 template <bool kKeyMod>
@@ -360,6 +374,9 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
   const bool short_keys = n_kv <= kShortKeyTiles;
   int pairs = 0;
   const int pair_mode = g_knobs[UVB_KNOB_FMHA_PAIR];       // 0 single CTAs, 1 pairs, 2 pairs with early S release
+  if (short_keys && g_knobs[UVB_KNOB_XATTN_PAIR] != 0) {
+    if ((rc = xattn_pair_workers<kKeyMod>(sms, &pairs)) != UVB_OK) return rc;
+  }
   if (!short_keys && !kKeyMod && pair_mode != 0) {
 #ifdef UVB_LAB_VARIANTS
     if (pair_mode == 2) {
@@ -418,7 +435,12 @@ int launch_fmha(const void* q, const void* k, const void* v, void* o, const int3
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // (the kernels' max dynamic shared memory was set by fmha_pair_workers)
+    // (the kernels' max dynamic shared memory was set by *_pair_workers)
+    if (short_keys) {
+      cfg.dynamicSmemBytes = uvb::FmhaSmem<kShortPairStages, 2, 2>::kDynBytes;
+      UVB_CUDA(cudaLaunchKernelEx(&cfg, uvb::fmha_fwd_kernel<kShortPairStages, 2, 2, kKeyMod>, p));
+      return UVB_OK;
+    }
 #ifdef UVB_LAB_VARIANTS
     if (pair_mode == 2) {
       cfg.dynamicSmemBytes = uvb::FmhaSmem<pair_stages<true>(), 1, 2, true>::kDynBytes;

@@ -72,14 +72,16 @@ constexpr int kWsSlotFloats = kWsOFloats + 2 * kUnitRows;
 // prefetched while the current one is computed and its O tile drains through the other buffer.
 template <int kStages, int kQBufs, int kCtas = 1, bool kEarlyS = false>
 struct FmhaSmem {
-  static_assert(kCtas == 1 || (kCtas == 2 && kQBufs == 1), "CTA pairs exist for the long-key variant only");
-  static_assert(!kEarlyS || kQBufs == 1, "early S release needs the shared-memory P panels");
+  static_assert(kCtas == 1 || kCtas == 2, "one CTA or a CTA pair");
+  static_assert(!kEarlyS || kQBufs == 1, "early S release exists for the long-key variant only");
   static constexpr int kStageBytes = kTileBytes / kCtas;   // a pair CTA stages half of every K / V tile
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = kQBufs * kQTiles * kTileBytes;
-  // kQBufs == 1 (long key sequences): the second 64-key half of P goes through shared memory (16 KiB per query
-  // tile, K-major SWIZZLE_128B like Q) so that the next score tile can be issued before it is consumed
-  static constexpr bool kPSmem = kQBufs == 1;
+  // The second 64-key half of P goes through shared memory (16 KiB per query tile, K-major SWIZZLE_128B like Q) so
+  // that the next score tile can be issued before it is consumed -- whenever the panels fit: always for the
+  // long-key variant (one query-block buffer), and for the query-block-pipelined short-key variant when it runs as
+  // CTA pairs (half-size K/V stages leave room for two Q/O buffers AND the panels)
+  static constexpr bool kPSmem = kQBufs == 1 || kCtas == 2;
   static constexpr int kPOff = kKvOff + kStages * kStageBytes;
   // kEarlyS: BOTH 64-key halves of P go through shared memory (two 16 KiB panels per query tile), nothing of P
   // aliases S_t any more, and S_t is handed back to the MMA warp as soon as the softmax holds it in registers

@@ -617,7 +617,8 @@ static void apply_knobs() {
   const char* e = getenv("UVB_KNOBS");
   if (e == nullptr) return;
   static const char* names[UVB_KNOB_COUNT] = {"fmha_pair", "fmha_split", "gemm_ctas", "gemm_bn", "gemm_small",
-                                              "prologue_pair", "fmha_poly", "sp_wait_timeout_s"};
+                                              "prologue_pair", "fmha_poly", "sp_wait_timeout_s",
+                                              "xattn_pair"};
   std::vector<char> buf(e, e + strlen(e) + 1);
   for (char* tok = strtok(buf.data(), ","); tok != nullptr; tok = strtok(nullptr, ",")) {
     char* eq = strchr(tok, '=');
