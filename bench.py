@@ -479,6 +479,27 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
             "frac": pbytes / (pavg * 1e-3) * 1e-9 / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
             "avg_launch_ms": pavg, "bytes_per_launch": pbytes, "traffic": traffic.get("prologue_dram_bytes_per_launch")}
 
+    # ---------------- the prologue kernel back to back (rotating input sets >> L2): its own sustained rate, without
+    # the event gaps of a 0.1-0.7 ms kernel between two attention launches and at the clock a memory-bound kernel gets
+    if "roofline_prologue" in res:
+        n_p = 24
+        for i in range(3):
+            _ext.qk_norm_rope(sets[i % n_sets]["q"], sets[i % n_sets]["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(n_p):
+            t = sets[i % n_sets]
+            _ext.qk_norm_rope(t["q"], t["k"], wn, wn, 1e-6, heads, cos_sin=cs, grid_sizes=grid)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / n_p
+        pb = res["roofline_prologue"]["bytes_per_launch"]
+        res["roofline_prologue"]["in_step"] = {k: res["roofline_prologue"][k] for k in ("achieved", "frac", "avg_launch_ms")}
+        res["roofline_prologue"]["back_to_back"] = {
+            "achieved": pb / (pms * 1e-3) * 1e-9, "frac": pb / (pms * 1e-3) * 1e-9 / peaks["hbm_gbs"], "avg_launch_ms": pms,
+            "launches": n_p, "what": "same kernel, same shapes, 4 rotating input sets (each >> L2), no other kernel in between"}
+
     # ---------------- the block's largest GEMM (ffn[0] + tanh-GELU), timed live -----
     if gemm_roofline and world == 1:
         ffn = cfg["ffn"]
