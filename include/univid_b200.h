@@ -244,7 +244,10 @@ int uvb_linear_bf16_sp(const void* x, const void* w, const float* bias, void* co
  *   m_t  = x - sigma * v
  *   x_c  = corrector_order ? c_a * last - c_b * m0 - c_ab * ([c_rho0 * (m1 - m0) / c_rk +] c_rho_last * (m_t - m0)) : x
  *   next = p_a * x_c - p_b * m_t [- p_ab * (p_rho0 * (m0 - m_t) / p_rk)]          (bracket: order 2)
- * with every operation individually rounded (bit-identical to the fp32 reference chain).
+ * with every operation individually rounded (bit-identical to the fp32 reference chain).  history_bf16 != 0
+ * reproduces what the same code computes inside torch.amp.autocast('cuda', bfloat16), where the product runs it
+ * (textimage2video.py:330-331): torch.einsum over the history terms (fm_solvers_unipc.py:471, :614) then runs in bf16 --
+ * rho and D1 are rounded to bf16, so is their product, and in the predictor alpha_t * B_h meets it in a bf16 multiply.
  *   cond, uncond (or NULL), x, last, m0, m1: DEVICE fp32 [n], 16-byte aligned; last/m0/m1 may be NULL when the orders
  *   do not need them.  m_out, xc_out, x_next: DEVICE fp32 [n] outputs (must not alias the inputs of later steps the
  *   caller still needs).  coef: HOST pointer.
@@ -256,6 +259,7 @@ typedef struct uvb_unipc_coef {
   float c_a, c_b, c_ab, c_rk, c_rho0, c_rho_last;
   int32_t predictor_order;   /* 1 or 2 */
   float p_a, p_b, p_ab, p_rk, p_rho0;
+  int32_t history_bf16;      /* 0: fp32 chain; 1: the bf16 roundings of the history einsum under bf16 autocast */
 } uvb_unipc_coef;
 int uvb_unipc_step(const float* cond, const float* uncond, const float* x, const float* last, const float* m0,
                    const float* m1, float* m_out, float* xc_out, float* x_next, int64_t n,

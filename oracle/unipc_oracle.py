@@ -83,9 +83,17 @@ class UniPCOracle:
     """Functional restatement of FlowUniPCMultistepScheduler.step for solver_order <= 3."""
 
     def __init__(self, num_train_timesteps=1000, solver_order=2, solver_type="bh2", init_shift=1.0,
-                 lower_order_final=True):
+                 lower_order_final=True, history_bf16=False):
+        """history_bf16: restate what the reference computes inside torch.amp.autocast('cuda', bfloat16), where the
+        product runs its sampling loop (textimage2video.py:330-331): torch.einsum over the history terms (:471, :614)
+        is an autocast op, so rho and D1 are rounded to bf16 and the result is bf16; in the predictor that bf16 tensor
+        then meets the 0-dim fp32 tensor alpha_t * B_h in a multiply whose result type is bf16 (a zero-dim operand of
+        the same category does not promote; it is rounded to bf16 first).  Pinned on the GPU box against the staged
+        reference scheduler run under CUDA autocast (tests/test_unipc_gpu.py); the CPU reference does not take this
+        route (einsum is not a CPU autocast op), so there is no CPU golden for it."""
         self.T, self.solver_order, self.solver_type = num_train_timesteps, solver_order, solver_type
         self.init_shift, self.lower_order_final = init_shift, lower_order_final
+        self.history_bf16 = history_bf16
 
     def set_timesteps(self, num_inference_steps, shift=1.0):
         self.timesteps, self.sigmas = sampling_schedule(num_inference_steps, shift, self.T, self.init_shift)
@@ -94,6 +102,11 @@ class UniPCOracle:
         self.last_sample = None
         self.step_index = None
         self.this_order = None
+
+    @staticmethod
+    def _einsum_bf16(rho, d1):
+        """One term of einsum('k,bkc...->bc...') under bf16 autocast: operands rounded to bf16, product rounded to bf16."""
+        return (rho.to(torch.bfloat16).float() * d1.to(torch.bfloat16).float()).to(torch.bfloat16)
 
     def _d1s(self, m0, rks):
         return [(self.model_outputs[-(k + 2)] - m0) / rk for k, rk in enumerate(rks)]
@@ -112,7 +125,7 @@ class UniPCOracle:
             x_t_ = c["a"] * self.last_sample - c["b"] * m0
             corr = 0
             for rho, d1 in zip(c["rhos"][:-1], self._d1s(m0, c["rks"])):
-                corr = corr + rho * d1
+                corr = corr + (self._einsum_bf16(rho, d1).float() if self.history_bf16 else rho * d1)
             sample = x_t_ - c["ab"] * (corr + c["rhos"][-1] * (m_t - m0))
         self.model_outputs = self.model_outputs[1:] + [m_t]       # :707-712
         order = min(self.solver_order, len(self.timesteps) - i) if self.lower_order_final else self.solver_order
@@ -123,8 +136,11 @@ class UniPCOracle:
         x_t_ = p["a"] * sample - p["b"] * m_t
         pred = 0
         for rho, d1 in zip(p["rhos"], self._d1s(m_t, p["rks"])):
-            pred = pred + rho * d1
-        prev = x_t_ - p["ab"] * pred
+            pred = pred + (self._einsum_bf16(rho, d1) if self.history_bf16 else rho * d1)
+        if self.history_bf16 and torch.is_tensor(pred):
+            prev = x_t_ - (p["ab"].to(torch.bfloat16) * pred).float()      # bf16 multiply, then fp32 subtract
+        else:
+            prev = x_t_ - p["ab"] * pred
         if self.lower_order_nums < self.solver_order:
             self.lower_order_nums += 1
         self.step_index += 1

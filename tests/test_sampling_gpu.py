@@ -60,13 +60,14 @@ def test_batched_cfg_forward_equals_two_forwards(setup, calls):
 
 def test_short_sampling_loop_follows_the_oracle_scheduler(setup):
     """4 UniPC steps, batched CFG + fused scheduler kernel: at every step the next latent equals the oracle scheduler
-    fed with the SAME two model outputs (bit-exact: the update is op-by-op rounded fp32)."""
+    fed with the SAME two model outputs (bit-exact: the update is op-by-op rounded, with the bf16 roundings of the
+    history term that bf16 autocast implies)."""
     t2v = importlib.import_module("univid_b200.wan.textimage2video")
     sched_mod = importlib.import_module("univid_b200.wan.utils.fm_solvers_unipc")
     model, latent, ctx, ctx_null, seq_len = setup
     sch = sched_mod.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
     sch.set_timesteps(4, device="cuda", shift=5.0)
-    o = uo.UniPCOracle()
+    o = uo.UniPCOracle(history_bf16=True)      # the loop runs under bf16 autocast like the product's: bf16 history einsum
     o.set_timesteps(4, shift=5.0)
     x, xo = latent, latent.cpu().unsqueeze(0)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):

@@ -75,3 +75,57 @@ def test_step_returns_the_reference_types_and_rejects_cpu():
     assert hasattr(out, "prev_sample") and out.prev_sample.shape == x.shape
     with pytest.raises(RuntimeError):
         sch.step(torch.randn(SHAPE), sch.timesteps[1], torch.randn(SHAPE))
+
+
+def test_history_bf16_mode_matches_the_oracle_bit_exactly():
+    """Inside torch.amp.autocast('cuda', bfloat16) the drop-in mirrors the bf16 einsum of the history terms (the
+    product's configuration); outside it stays on the fp32 chain.  Both against the oracle."""
+    steps, shift = 12, 5.0
+    for autocast in (True, False):
+        sch, o = _sched(), uo.UniPCOracle(history_bf16=autocast)
+        sch.set_timesteps(steps, device="cuda", shift=shift)
+        o.set_timesteps(steps, shift=shift)
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(SHAPE, generator=g)
+        xg = x.cuda()
+        for k, t in enumerate(sch.timesteps):
+            v = torch.randn(SHAPE, generator=g)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                xg = sch.step(v.cuda(), t, xg, return_dict=False)[0]
+            x = o.step(v, o.timesteps[k], x)
+            assert xg.dtype == torch.float32
+            assert torch.equal(xg.cpu(), x), (autocast, k, (xg.cpu() - x).abs().max())
+
+
+def test_history_bf16_mode_matches_the_reference_scheduler_under_cuda_autocast():
+    """The UNMODIFIED reference FlowUniPCMultistepScheduler (staged under oracle/_ref) run on the GPU inside
+    torch.amp.autocast('cuda', bfloat16) -- the way textimage2video.py:330-331 runs it -- against the drop-in under the
+    same context: every step of a 20-step schedule.  The reference evaluates its scalar coefficients on the GPU
+    (device libm), the drop-in on the host, so the bar is 1e-5 relative to the sample scale rather than bit equality;
+    the bf16 roundings themselves are 4e-3 apart from the fp32 chain, i.e. the test separates the two modes."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference sources not staged (python oracle/make_ref.py)")
+    Ref = ref_loader.load_unipc_scheduler()
+    steps, shift = 20, 5.0
+    ref = Ref(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    ref.set_timesteps(steps, device="cuda", shift=shift)
+    sch, sch32 = _sched(), _sched()
+    sch.set_timesteps(steps, device="cuda", shift=shift)
+    sch32.set_timesteps(steps, device="cuda", shift=shift)
+    sch32.history_dtype = "fp32"
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(SHAPE, generator=g).cuda()
+    xr, xs, x32 = x, x, x
+    worst, worst32 = 0.0, 0.0
+    for t in ref.timesteps:
+        v = torch.randn(SHAPE, generator=g).cuda()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            xr = ref.step(v, t, xr, return_dict=False)[0]
+            xs = sch.step(v, t, xs, return_dict=False)[0]
+            x32 = sch32.step(v, t, x32, return_dict=False)[0]
+        scale = xr.abs().max().item()
+        worst = max(worst, (xr.float() - xs).abs().max().item() / scale)
+        worst32 = max(worst32, (xr.float() - x32).abs().max().item() / scale)
+    assert worst <= 1e-5, (worst, worst32)
+    assert worst32 > 10 * max(worst, 1e-7), (worst, worst32)      # the fp32 chain is measurably NOT what autocast computes

@@ -19,7 +19,7 @@ EXPORTS = (
     "uvb_sp_wait", "uvb_block_glue", "uvb_linear_bf16", "uvb_unipc_step", "uvb_set_knob", "uvb_get_knob",
     "uvb_linear_bf16_sp", "uvb_sp_signal_wait",
 )
-ABI_VERSION = 109
+ABI_VERSION = 110
 KNOBS = {"fmha_pair": 0, "fmha_split": 1, "gemm_ctas": 2, "gemm_bn": 3, "gemm_small": 4, "prologue_pair": 5,
          "fmha_poly": 6, "sp_wait_timeout_s": 7, "xattn_pair": 8}
 
@@ -33,7 +33,7 @@ class UnipcCoef(_c.Structure):
     """uvb_unipc_coef (include/univid_b200.h)."""
     _fields_ = [("guide_scale", _f), ("sigma", _f), ("corrector_order", _c.c_int32), ("c_a", _f), ("c_b", _f),
                 ("c_ab", _f), ("c_rk", _f), ("c_rho0", _f), ("c_rho_last", _f), ("predictor_order", _c.c_int32),
-                ("p_a", _f), ("p_b", _f), ("p_ab", _f), ("p_rk", _f), ("p_rho0", _f)]
+                ("p_a", _f), ("p_b", _f), ("p_ab", _f), ("p_rk", _f), ("p_rho0", _f), ("history_bf16", _c.c_int32)]
 
 
 launch_count = 0   # kernels launched through this module (bench.py reports it as gpu_launches)

@@ -583,7 +583,7 @@ int linear_impl(const void* x, const void* w, const float* bias, void* y, int M,
 
 extern "C" {
 
-int uvb_version(void) { return 109; }
+int uvb_version(void) { return 110; }
 
 int uvb_set_knob(int knob, int value) {
   if (knob < 0 || knob >= UVB_KNOB_COUNT) return fail(UVB_ERR_INVALID, "unknown knob %d", knob);
@@ -968,6 +968,7 @@ int uvb_unipc_step(const float* cond, const float* uncond, const float* x, const
   p.p_ab = coef->p_ab;
   p.p_rk = coef->p_rk;
   p.p_rho0 = coef->p_rho0;
+  p.history_bf16 = coef->history_bf16 != 0 ? 1 : 0;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 8LL * sms) blocks = 8LL * sms;       // grid-stride: a whole number of CTAs per SM

@@ -9,7 +9,15 @@
 // rounded IEEE fp32 op in the reference's order (no FMA contraction), so the result is bit-identical to the
 // reference evaluated op by op in fp32.  Pure HBM streaming: 6 reads + 3 writes of 4 bytes per latent element
 // (the eager chain is ~25 launches and ~100 bytes per element).
+//
+// history_bf16: the product runs the scheduler inside torch.amp.autocast('cuda', bf16) (textimage2video.py:330-331),
+// under which the reference's torch.einsum over the history terms (:471, :614) runs in bf16 on the GPU: its operands
+// (rho, D1) are rounded to bf16, the product is rounded to bf16, and in the predictor the bf16 result meets the 0-dim
+// fp32 tensor alpha_t * B_h in a bf16 multiply (type promotion keeps the dimensioned operand's dtype, the scalar is
+// rounded to bf16 first).  With history_bf16 != 0 the kernel reproduces exactly those roundings; with 0 it is the
+// fp32 chain the reference computes outside autocast (and on the CPU).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,7 +39,10 @@ struct SamplerStepParams {
   float c_a, c_b, c_ab, c_rk, c_rho0, c_rho_last;
   int pred_order;        // 1 or 2
   float p_a, p_b, p_ab, p_rk, p_rho0;
+  int history_bf16;      // reproduce the bf16 einsum of the history terms under the product's autocast
 };
+
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 __device__ __forceinline__ void sampler_step_elem(const SamplerStepParams& p, float vc, float vu, float x, float last,
                                                   float m0, float m1, float& m_t, float& xs, float& xn) {
@@ -41,13 +52,26 @@ __device__ __forceinline__ void sampler_step_elem(const SamplerStepParams& p, fl
   if (p.corr_order > 0) {
     const float xt = __fsub_rn(__fmul_rn(p.c_a, last), __fmul_rn(p.c_b, m0));
     float inner = __fmul_rn(p.c_rho_last, __fsub_rn(m_t, m0));
-    if (p.corr_order == 2) inner = __fadd_rn(__fmul_rn(p.c_rho0, __fdiv_rn(__fsub_rn(m1, m0), p.c_rk)), inner);
+    if (p.corr_order == 2) {
+      const float d1 = __fdiv_rn(__fsub_rn(m1, m0), p.c_rk);
+      const float hist = p.history_bf16 ? round_bf16(__fmul_rn(round_bf16(p.c_rho0), round_bf16(d1)))   // bf16 einsum
+                                        : __fmul_rn(p.c_rho0, d1);
+      inner = __fadd_rn(hist, inner);
+    }
     xs = __fsub_rn(xt, __fmul_rn(p.c_ab, inner));
   }
   const float pt = __fsub_rn(__fmul_rn(p.p_a, xs), __fmul_rn(p.p_b, m_t));
   xn = pt;
-  if (p.pred_order == 2)
-    xn = __fsub_rn(pt, __fmul_rn(p.p_ab, __fmul_rn(p.p_rho0, __fdiv_rn(__fsub_rn(m0, m_t), p.p_rk))));
+  if (p.pred_order == 2) {
+    const float d1 = __fdiv_rn(__fsub_rn(m0, m_t), p.p_rk);
+    if (p.history_bf16) {
+      // pred_res = einsum(rho, D1) in bf16; alpha_t * B_h (0-dim fp32) * pred_res (bf16) is a bf16 multiply
+      const float pred = round_bf16(__fmul_rn(round_bf16(p.p_rho0), round_bf16(d1)));
+      xn = __fsub_rn(pt, round_bf16(__fmul_rn(round_bf16(p.p_ab), pred)));
+    } else {
+      xn = __fsub_rn(pt, __fmul_rn(p.p_ab, __fmul_rn(p.p_rho0, d1)));
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerStepParams p) {

@@ -70,6 +70,9 @@ class FlowUniPCMultistepScheduler:
             disable_corrector=disable_corrector, solver_p=solver_p, timestep_spacing=timestep_spacing,
             steps_offset=steps_offset, final_sigmas_type=final_sigmas_type)
         self.predict_x0 = predict_x0
+        # "auto": mirror the reference under the ambient autocast state (bf16 einsum of the history terms inside
+        # torch.amp.autocast('cuda', bfloat16), fp32 otherwise); "fp32" / "bf16" pin it.  Not a reference argument.
+        self.history_dtype = "auto"
         self.num_inference_steps = None
         alphas = np.linspace(1, 1 / num_train_timesteps, num_train_timesteps)[::-1].copy()
         sigmas = torch.from_numpy(1.0 - alphas).to(dtype=torch.float32)
@@ -164,6 +167,13 @@ class FlowUniPCMultistepScheduler:
             self._init_step_index(timestep)
         i = self._step_index
         coef = _ext.UnipcCoef()
+        # Inside torch.amp.autocast('cuda', bfloat16) -- where the product runs the sampling loop, textimage2video.py:
+        # 330-331 -- the reference's einsum over the history terms executes in bf16 on the GPU; mirror its roundings.
+        # (history_dtype = "fp32" / "bf16" overrides the detection.)
+        if self.history_dtype == "auto":
+            coef.history_bf16 = int(torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16)
+        else:
+            coef.history_bf16 = int(self.history_dtype == "bf16")
         coef.guide_scale = float(guide_scale)
         coef.sigma = float(self.sigmas[i])
         use_corrector = i > 0 and (i - 1) not in self.disable_corrector and self.last_sample is not None
