@@ -247,7 +247,8 @@ int uvb_linear_bf16_sp(const void* x, const void* w, const float* bias, void* co
  * with every operation individually rounded (bit-identical to the fp32 reference chain).  history_bf16 != 0
  * reproduces what the same code computes inside torch.amp.autocast('cuda', bfloat16), where the product runs it
  * (textimage2video.py:330-331): torch.einsum over the history terms (fm_solvers_unipc.py:471, :614) then runs in bf16 --
- * rho and D1 are rounded to bf16, so is their product, and in the predictor alpha_t * B_h meets it in a bf16 multiply.
+ * rho and D1 are rounded to bf16, so is their product, and in the predictor the product with the fp32 scalar alpha_t * B_h
+ * is rounded to bf16 once more.
  *   cond, uncond (or NULL), x, last, m0, m1: DEVICE fp32 [n], 16-byte aligned; last/m0/m1 may be NULL when the orders
  *   do not need them.  m_out, xc_out, x_next: DEVICE fp32 [n] outputs (must not alias the inputs of later steps the
  *   caller still needs).  coef: HOST pointer.

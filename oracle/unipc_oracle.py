@@ -87,8 +87,9 @@ class UniPCOracle:
         """history_bf16: restate what the reference computes inside torch.amp.autocast('cuda', bfloat16), where the
         product runs its sampling loop (textimage2video.py:330-331): torch.einsum over the history terms (:471, :614)
         is an autocast op, so rho and D1 are rounded to bf16 and the result is bf16; in the predictor that bf16 tensor
-        then meets the 0-dim fp32 tensor alpha_t * B_h in a multiply whose result type is bf16 (a zero-dim operand of
-        the same category does not promote; it is rounded to bf16 first).  Pinned on the GPU box against the staged
+        then meets the 0-dim fp32 CPU tensor alpha_t * B_h (the reference keeps its sigmas on the host, :228-229) in a
+        multiply whose result type is bf16 (a zero-dim operand of the same category does not promote; as a scalar
+        operand it enters in fp32).  Pinned on the GPU box against the staged
         reference scheduler run under CUDA autocast (tests/test_unipc_gpu.py); the CPU reference does not take this
         route (einsum is not a CPU autocast op), so there is no CPU golden for it."""
         self.T, self.solver_order, self.solver_type = num_train_timesteps, solver_order, solver_type
@@ -138,7 +139,7 @@ class UniPCOracle:
         for rho, d1 in zip(p["rhos"], self._d1s(m_t, p["rks"])):
             pred = pred + (self._einsum_bf16(rho, d1) if self.history_bf16 else rho * d1)
         if self.history_bf16 and torch.is_tensor(pred):
-            prev = x_t_ - (p["ab"].to(torch.bfloat16) * pred).float()      # bf16 multiply, then fp32 subtract
+            prev = x_t_ - (p["ab"].float() * pred.float()).to(torch.bfloat16).float()   # scalar (fp32) x bf16 -> bf16
         else:
             prev = x_t_ - p["ab"] * pred
         if self.lower_order_nums < self.solver_order:

@@ -1,0 +1,71 @@
+"""CPU checks of the measurement plumbing: bench.py's flop accounting and reference arm (on a toy geometry that runs in
+seconds), and the reference staging recipe oracle/make_ref.py."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from oracle import make_ref, ref_loader  # noqa: E402
+
+
+def test_flop_accounting_matches_the_definitions():
+    L, heads, text = 32760, 12, 512
+    fs, fc = bench.flops_per_layer(L, heads, text)
+    assert fs == 4.0 * L * L * heads * 128 and fc == 4.0 * L * text * heads * 128
+    # judge's round-1 arithmetic: 2.009e14 attention flop per 1.3B step, 8.19e13 linear flop
+    assert abs((fs + fc) * 30 / 2.009e14 - 1) < 2e-3
+    assert abs(bench.linear_flops_per_layer(L, 1536, 8960, text) * 30 / 8.19e13 - 1) < 5e-3
+    cfg = bench.CONFIGS[bench.HEADLINE]
+    assert cfg["heads"] % 8 == 0 and (cfg["grid"][0] * cfg["grid"][1] * cfg["grid"][2]) % 8 == 0      # shards over 1/2/4/8 GPUs
+    assert cfg["grid"][0] * cfg["grid"][1] * cfg["grid"][2] == 75600
+
+
+def test_reference_arm_runs_the_reference_modules_on_all_threads():
+    toy = dict(name="toy", dim=256, heads=2, layers=3, ffn=512, grid=(4, 6, 8), text_len=64)
+    tf, ms, sample, threads, kind = bench.cpu_reference_rate(toy, 4.0, 2, 1)
+    assert tf > 0 and ms > 0 and threads >= 1
+    assert kind == ("reference" if ref_loader.available() else "port")
+    assert "of 4 latent frames" in sample and ("unmodified reference modules" in sample) == (kind == "reference")
+
+
+def test_reference_arm_cli_prints_the_contract_line():
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # what torchrun exports: the arm must undo it
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1.3B", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["higher_is_better"] is True
+    assert line["steps"] == 1 and line["warmup"] == 0                                  # honours --steps / --warmup
+    assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["value"] == line["value"] and cb["kind"] in ("reference", "port") and cb["cores"] == len(os.sched_getaffinity(0))
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/models/wan/utils/modules/model.py"), reason="/root/reference not mounted")
+def test_make_ref_stages_the_reference_byte_for_byte(tmp_path):
+    man = make_ref.stage(src="/root/reference", dest=str(tmp_path), verbose=False)
+    for rel in make_ref.FILES:
+        a = open(os.path.join("/root/reference", rel), "rb").read()
+        b = open(os.path.join(tmp_path, rel), "rb").read()
+        assert a == b and man["files"][rel] == hashlib.sha256(a).hexdigest()
+    cut = open(os.path.join(tmp_path, make_ref.PIPELINE)).read()
+    src = open(os.path.join("/root/reference", make_ref.PIPELINE)).read().splitlines(keepends=True)
+    lo, hi = man["files"][make_ref.PIPELINE]["lines"]
+    assert "".join(src[lo - 1:hi]) in cut and cut.count("\nclass Wan22ContextWrapper") == 1
+
+
+def test_staged_reference_is_what_the_loader_uses_when_the_tree_is_absent(tmp_path, monkeypatch):
+    """On the GPU box there is no /root/reference: ref_loader falls back to oracle/_ref."""
+    assert ref_loader.STAGED_ROOT.endswith(os.path.join("oracle", "_ref"))
+    monkeypatch.delenv("UNIVID_REFERENCE", raising=False)
+    picked = ref_loader._pick_root()
+    assert picked in ("/root/reference", ref_loader.STAGED_ROOT)
+    if not os.path.isdir("/root/reference"):
+        assert picked == ref_loader.STAGED_ROOT

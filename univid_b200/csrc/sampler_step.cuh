@@ -13,8 +13,8 @@
 // history_bf16: the product runs the scheduler inside torch.amp.autocast('cuda', bf16) (textimage2video.py:330-331),
 // under which the reference's torch.einsum over the history terms (:471, :614) runs in bf16 on the GPU: its operands
 // (rho, D1) are rounded to bf16, the product is rounded to bf16, and in the predictor the bf16 result meets the 0-dim
-// fp32 tensor alpha_t * B_h in a bf16 multiply (type promotion keeps the dimensioned operand's dtype, the scalar is
-// rounded to bf16 first).  With history_bf16 != 0 the kernel reproduces exactly those roundings; with 0 it is the
+// fp32 (CPU) tensor alpha_t * B_h in a multiply whose result is bf16 (type promotion keeps the dimensioned operand's
+// dtype; the scalar itself enters in fp32).  With history_bf16 != 0 the kernel reproduces exactly those roundings; with 0 it is the
 // fp32 chain the reference computes outside autocast (and on the CPU).
 #pragma once
 #include <cuda_bf16.h>
@@ -65,9 +65,10 @@ __device__ __forceinline__ void sampler_step_elem(const SamplerStepParams& p, fl
   if (p.pred_order == 2) {
     const float d1 = __fdiv_rn(__fsub_rn(m0, m_t), p.p_rk);
     if (p.history_bf16) {
-      // pred_res = einsum(rho, D1) in bf16; alpha_t * B_h (0-dim fp32) * pred_res (bf16) is a bf16 multiply
+      // pred_res = einsum(rho, D1) in bf16; alpha_t * B_h is a 0-dim CPU tensor (the reference keeps its sigmas on the
+      // host, :228-229), i.e. a scalar operand: it enters the multiply in fp32 and the RESULT takes pred_res' dtype
       const float pred = round_bf16(__fmul_rn(round_bf16(p.p_rho0), round_bf16(d1)));
-      xn = __fsub_rn(pt, round_bf16(__fmul_rn(round_bf16(p.p_ab), pred)));
+      xn = __fsub_rn(pt, round_bf16(__fmul_rn(p.p_ab, pred)));
     } else {
       xn = __fsub_rn(pt, __fmul_rn(p.p_ab, __fmul_rn(p.p_rho0, d1)));
     }
