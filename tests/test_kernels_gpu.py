@@ -93,6 +93,18 @@ def test_streaming_prologue_is_bit_identical_to_the_row_kernels(ext, heads, b, l
     torch.cuda.synchronize()
     for mode in (1, 2):
         assert torch.equal(outs[mode][0], outs[0][0]) and torch.equal(outs[mode][1], outs[0][1]), mode
+    # q alone (the query prologue of cross-attention; >= 4096 rows take the streaming kernel): norm only and norm + rope
+    ql = torch.randn(1, 4500, dim, generator=g).to(torch.bfloat16).to(dev)
+    gl = [(15, 10, 30)]
+    for kwq in (dict(), dict(cos_sin=cs, grid_sizes=gl)):
+        got = {}
+        for mode in (0, 2):
+            old = ext.set_knob("prologue_pair", mode)
+            try:
+                got[mode] = ext.qk_norm_rope(ql, None, wq, None, 1e-6, heads, **kwq)[0]
+            finally:
+                ext.set_knob("prologue_pair", old)
+        assert torch.equal(got[0], got[2])
     # rotation only (qk_norm=False)
     old = ext.set_knob("prologue_pair", 2)
     try:

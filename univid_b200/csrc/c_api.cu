@@ -479,9 +479,10 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
   const dim3 block(uvb::kNormRopeWarps * 32);
   // q and k together (self-attention): one warp group per token, both rows in flight (UVB_KNOB_PROLOGUE_PAIR = 0
   // keeps the one-row-per-group kernel)
-  // Self-attention form at the product's widths: the streaming kernel (persistent CTAs, bulk-copy ring)
-  if (g_knobs[UVB_KNOB_PROLOGUE_PAIR] == 2 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&
-      p.row_scale == nullptr && sizeof(InT) == 2 && (dim == 1536 || dim == 3072 || dim == 5120)) {
+  // bf16 rows at the product's widths without the affine pre-map: the streaming kernel (persistent CTAs, bulk-copy
+  // ring) -- q and k together (self-attention) or q alone (the query prologue of cross-attention)
+  if (g_knobs[UVB_KNOB_PROLOGUE_PAIR] == 2 && p.q_in != nullptr && p.pre_bias == nullptr && p.row_scale == nullptr &&
+      sizeof(InT) == 2 && (dim == 1536 || dim == 3072 || dim == 5120)) {
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc != UVB_OK) return rc;
@@ -493,10 +494,18 @@ int launch_norm_rope_t(const uvb::NormRopeParams& p, cudaStream_t stream) {
       UVB_CUDA(cudaGetLastError());
       return UVB_OK;
     };
-    switch (dim) {
-      case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers>, uvb::StreamSmem<6, 1>::kDynBytes, uvb::StreamSmem<6, 1>::kRows);
-      case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers>, uvb::StreamSmem<6, 2>::kDynBytes, uvb::StreamSmem<6, 2>::kRows);
-      default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers>, uvb::StreamSmem<5, 4>::kDynBytes, uvb::StreamSmem<5, 4>::kRows);
+    if (p.k_in != nullptr) {
+      switch (dim) {
+        case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers>, uvb::StreamSmem<6, 1>::kDynBytes, uvb::StreamSmem<6, 1>::kRows);
+        case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers>, uvb::StreamSmem<6, 2>::kDynBytes, uvb::StreamSmem<6, 2>::kRows);
+        default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers>, uvb::StreamSmem<5, 4>::kDynBytes, uvb::StreamSmem<5, 4>::kRows);
+      }
+    } else if (static_cast<long long>(p.B) * p.L >= 4096) {      // a few hundred context rows stay on the row kernel
+      switch (dim) {
+        case 1536: return launch(uvb::qk_norm_rope_stream_kernel<6, 1, kPeers, false>, uvb::StreamSmem<6, 1, false>::kDynBytes, uvb::StreamSmem<6, 1, false>::kRows);
+        case 3072: return launch(uvb::qk_norm_rope_stream_kernel<6, 2, kPeers, false>, uvb::StreamSmem<6, 2, false>::kDynBytes, uvb::StreamSmem<6, 2, false>::kRows);
+        default: return launch(uvb::qk_norm_rope_stream_kernel<5, 4, kPeers, false>, uvb::StreamSmem<5, 4, false>::kDynBytes, uvb::StreamSmem<5, 4, false>::kRows);
+      }
     }
   }
   const bool pair = g_knobs[UVB_KNOB_PROLOGUE_PAIR] != 0 && p.q_in != nullptr && p.k_in != nullptr && p.pre_bias == nullptr &&

@@ -427,12 +427,13 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
-template <int VPL, int WPR>
+// kHasK = false: q only (the query prologue of cross-attention: norm, no rotation partner) -- a stage holds q rows only
+template <int VPL, int WPR, bool kHasK = true>
 struct StreamSmem {
   static constexpr int kDim = 256 * VPL * WPR;
   static constexpr int kRowBytes = kDim * 2;
   static constexpr int kRows = kStreamConsumerWarps / WPR;          // tokens per stage
-  static constexpr int kStageBytes = 2 * kRows * kRowBytes;         // q rows | k rows
+  static constexpr int kStageBytes = (kHasK ? 2 : 1) * kRows * kRowBytes;   // q rows | k rows
   static constexpr int kWeightBytes = 2 * kDim * 4;                 // wq | wk, fp32
   static constexpr int kFixed = kWeightBytes + 1024;                // + barriers, reduction scratch, alignment slack
   static constexpr int kStagesMax = (232448 - kFixed) / kStageBytes;
@@ -527,10 +528,10 @@ __device__ __forceinline__ void stream_row(const uint8_t* __restrict__ srow, con
   }
 }
 
-template <int VPL, int WPR, bool kPeers>
+template <int VPL, int WPR, bool kPeers, bool kHasK = true>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
-  using SM = StreamSmem<VPL, WPR>;
+  using SM = StreamSmem<VPL, WPR, kHasK>;
   constexpr int kStages = SM::kStages;
   constexpr int kRows = SM::kRows;
   extern __shared__ uint8_t stream_smem_raw[];
@@ -571,9 +572,9 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
         const long long nr = rows - r0 < kRows ? rows - r0 : kRows;
         const uint32_t bytes = static_cast<uint32_t>(nr) * SM::kRowBytes;
         uint8_t* dst = smem + slot * SM::kStageBytes;
-        mbar_arrive_expect_tx(&full[slot], 2 * bytes);
+        mbar_arrive_expect_tx(&full[slot], (kHasK ? 2 : 1) * bytes);
         bulk_load_1d(dst, qg + r0 * SM::kDim, bytes, &full[slot]);
-        bulk_load_1d(dst + kRows * SM::kRowBytes, kg + r0 * SM::kDim, bytes, &full[slot]);
+        if constexpr (kHasK) bulk_load_1d(dst + kRows * SM::kRowBytes, kg + r0 * SM::kDim, bytes, &full[slot]);
       }
       __syncwarp();
     }
@@ -618,9 +619,11 @@ qk_norm_rope_stream_kernel(const __grid_constant__ NormRopeParams p) {
         const uint8_t* sk = sq + kRows * SM::kRowBytes;
         stream_row<VPL, WPR, kPeers>(sq, w_s, normed_q, p.q_out + out_off, p.q_peer, out_off, p.hpg, p.out_sg, p.eps,
                                      rotate, cs, lane, red + group * WPR, 1 + group);
-        stream_row<VPL, WPR, kPeers>(sk, w_s + SM::kDim, normed_k, p.k_out + out_off, p.k_peer, out_off, p.hpg,
-                                     p.out_sg, p.eps, rotate, cs, lane, red + kStreamConsumerWarps + group * WPR,
-                                     1 + group);
+        if constexpr (kHasK) {
+          stream_row<VPL, WPR, kPeers>(sk, w_s + SM::kDim, normed_k, p.k_out + out_off, p.k_peer, out_off, p.hpg,
+                                       p.out_sg, p.eps, rotate, cs, lane, red + kStreamConsumerWarps + group * WPR,
+                                       1 + group);
+        }
       }
       // both rows of this warp's token have been read out of the stage
       __syncwarp();
