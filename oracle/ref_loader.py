@@ -1,8 +1,9 @@
 """Load the UNMODIFIED reference hot-path sources -- TEST INFRASTRUCTURE.
 
 From /root/reference when it is mounted (the build container: tests/golden/make_*.py, tests/test_reference_compat.py
-pin the oracle with it), otherwise from oracle/_ref/, the byte-for-byte staging of the same files that
-oracle/make_ref.py writes (git-ignored; it travels to the GPU box like a built .so, where bench.py's reference arm and
+pin the oracle with it), otherwise from the archive oracle/_ref/reference_hotpath.tar.gz that oracle/make_ref.py
+writes from the same files (git-ignored; it travels to the GPU box like a built .so, is unpacked into a temporary
+directory per process and verified against its sha256 manifest; bench.py's reference arm and
 tests/test_reference_binding_gpu.py use it).  The files are imported as they are (recipe: SURVEY.md sec. 8c).
 
   * a 4-symbol stub stands in for `diffusers` (only ConfigMixin / register_to_config / ModelMixin are
@@ -26,7 +27,24 @@ import torch
 import torch.nn as nn
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-STAGED_ROOT = os.path.join(_HERE, "_ref")          # written by oracle/make_ref.py (git-ignored, travels to the GPU box)
+STAGED_DIR = os.path.join(_HERE, "_ref")           # written by oracle/make_ref.py (git-ignored, travels to the GPU box)
+_UNPACKED = None
+
+
+def _staged_root():
+    """The staged archive unpacked into a per-process temporary directory (removed at exit), or a path that does not
+    exist when nothing was staged."""
+    global _UNPACKED
+    if _UNPACKED is None:
+        if not os.path.isfile(os.path.join(STAGED_DIR, "MANIFEST.json")):
+            return os.path.join(STAGED_DIR, "missing")
+        import atexit
+        import shutil
+        import tempfile
+        from oracle import make_ref
+        _UNPACKED = make_ref.unpack(tempfile.mkdtemp(prefix="uvb_ref_"), STAGED_DIR)
+        atexit.register(shutil.rmtree, _UNPACKED, True)
+    return _UNPACKED
 
 
 def _pick_root():
@@ -35,7 +53,7 @@ def _pick_root():
         return env
     if os.path.isfile("/root/reference/models/wan/utils/modules/model.py"):
         return "/root/reference"
-    return STAGED_ROOT
+    return _staged_root()
 
 
 REF_ROOT = _pick_root()

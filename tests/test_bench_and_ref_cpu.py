@@ -50,22 +50,34 @@ def test_reference_arm_cli_prints_the_contract_line():
 
 @pytest.mark.skipif(not os.path.isfile("/root/reference/models/wan/utils/modules/model.py"), reason="/root/reference not mounted")
 def test_make_ref_stages_the_reference_byte_for_byte(tmp_path):
-    man = make_ref.stage(src="/root/reference", dest=str(tmp_path), verbose=False)
+    man = make_ref.stage(src="/root/reference", dest=str(tmp_path / "stage"), verbose=False)
+    out = make_ref.unpack(str(tmp_path / "unpacked"), str(tmp_path / "stage"))
     for rel in make_ref.FILES:
         a = open(os.path.join("/root/reference", rel), "rb").read()
-        b = open(os.path.join(tmp_path, rel), "rb").read()
+        b = open(os.path.join(out, rel), "rb").read()
         assert a == b and man["files"][rel] == hashlib.sha256(a).hexdigest()
-    cut = open(os.path.join(tmp_path, make_ref.PIPELINE)).read()
+    cut = open(os.path.join(out, make_ref.PIPELINE)).read()
     src = open(os.path.join("/root/reference", make_ref.PIPELINE)).read().splitlines(keepends=True)
     lo, hi = man["files"][make_ref.PIPELINE]["lines"]
     assert "".join(src[lo - 1:hi]) in cut and cut.count("\nclass Wan22ContextWrapper") == 1
+    # a tampered archive is refused
+    import json as _json
+    mpath = tmp_path / "stage" / "MANIFEST.json"
+    m = _json.loads(mpath.read_text())
+    m["files"][make_ref.FILES[0]] = "0" * 64
+    mpath.write_text(_json.dumps(m))
+    with pytest.raises(RuntimeError, match="checksum"):
+        make_ref.unpack(str(tmp_path / "again"), str(tmp_path / "stage"))
 
 
-def test_staged_reference_is_what_the_loader_uses_when_the_tree_is_absent(tmp_path, monkeypatch):
-    """On the GPU box there is no /root/reference: ref_loader falls back to oracle/_ref."""
-    assert ref_loader.STAGED_ROOT.endswith(os.path.join("oracle", "_ref"))
+def test_staged_reference_is_what_the_loader_uses_when_the_tree_is_absent(monkeypatch):
+    """On the GPU box there is no /root/reference: ref_loader unpacks oracle/_ref/reference_hotpath.tar.gz."""
     monkeypatch.delenv("UNIVID_REFERENCE", raising=False)
     picked = ref_loader._pick_root()
-    assert picked in ("/root/reference", ref_loader.STAGED_ROOT)
-    if not os.path.isdir("/root/reference"):
-        assert picked == ref_loader.STAGED_ROOT
+    if os.path.isdir("/root/reference"):
+        assert picked == "/root/reference"
+    staged = ref_loader._staged_root()
+    if os.path.isfile(os.path.join(ref_loader.STAGED_DIR, "MANIFEST.json")):
+        assert os.path.isfile(os.path.join(staged, "models/wan/utils/modules/model.py"))
+        if not os.path.isdir("/root/reference"):
+            assert picked == staged
