@@ -349,7 +349,9 @@ class WanCrossAttention(WanSelfAttention):
             v_lin = _lin(self.v, context).float() - b_v
             val = (k_lin, v_lin, b_k, b_v)
         if cacheable:
-            if len(cache) >= 2 * self.context_cache_size:
+            for old in [k for k, v in cache.items() if v[0]() is None]:       # contexts that no longer exist
+                del cache[old]
+            if len(cache) >= 2 * self.context_cache_size:                      # plain / fused entries of each context
                 for old in list(cache.keys())[:len(cache) - 2 * self.context_cache_size + 1]:
                     del cache[old]
             cache[key] = (weakref.ref(context), val)
