@@ -1,4 +1,5 @@
 #!/bin/bash
+# ROUND-1 script, kept for the record (bench.py now defaults to the 14B headline; use scripts/gpu_r02b.sh + gpu_round2.sh).
 # One full GPU pass on 1 B200 (run under gpurun): parity tests, smoke, bench, kernel battery, ncu evidence.
 # Usage: bash scripts/gpu_round.sh [tag]
 TAG=${1:-r01}
@@ -41,8 +42,5 @@ echo "== denoise step by category (CUDA events)"
 python scripts/profile_denoise.py > gpurun_out/denoise_profile_$TAG.log 2>&1; cat gpurun_out/denoise_profile_$TAG.log
 echo "== sampler step / batched CFG / per-token timesteps"
 python scripts/bench_cfg_batch.py > gpurun_out/cfg_batch_$TAG.log 2>&1; tail -4 gpurun_out/cfg_batch_$TAG.log
-echo "== A/B inside the power-capped step: exp2 on the FMA pipe for 1 pair in 4 (UVB_FMHA_POLY=4) vs MUFU only"
-for v in 0 4 0 4; do
-  UVB_FMHA_POLY=$v timeout 300 python bench.py --steps 3 --warmup 3 --skip-cpu --skip-denoise 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('POLY=$v value', round(d['value'],1), 'fmha in-step', round(d['roofline']['achieved'],1), 'clk', d['clocks']['sm_mhz'])"
-done | tee gpurun_out/poly_ab_$TAG.log
+# (round-1 in-step A/B of the FMA-pipe exp2 removed: the variant lives in the lab build only; see scripts/gpu_round2.sh for the round-2 A/Bs via bench.py --knob)
 ls -la gpurun_out | tail -20
