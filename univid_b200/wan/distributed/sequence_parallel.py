@@ -49,6 +49,12 @@ def rope_apply(x, grid_sizes, freqs):
     return out.float()
 
 
+def _plain_blocks(model, x, kwargs):
+    for block in model.blocks:
+        x = block(x, **kwargs)
+    return x
+
+
 def sp_dit_forward(
     self,
     x,
@@ -75,8 +81,7 @@ def sp_dit_forward(
     elif e.size(1) > 1:   # per-token timesteps: shard the modulation with the tokens
         e = torch.chunk(e, world, dim=1)[rank]
         kwargs['e'] = torch.chunk(kwargs['e'], world, dim=1)[rank]
-    for block in self.blocks:
-        x = block(x, **kwargs)
+    x = self._run_blocks(x, kwargs) if hasattr(self, '_run_blocks') else _plain_blocks(self, x, kwargs)
     x = self.head(x, self.token_embedding(e, kwargs.get('e_index')))
     x = gather_forward(x, dim=1)
     x = self.unpatchify(x, kwargs['grid_sizes'])
