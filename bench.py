@@ -174,11 +174,22 @@ def cpu_reference_rate(cfg, seconds_budget, steps, warmup):
     t_probe2, _ = run(1)
     t_probe = min(t_probe, t_probe2)
     per_step_budget = seconds_budget / max(steps + warmup, 1)
-    frames = 1
-    for cand in range(f, 0, -1):       # self-attention time grows ~quadratically with the token count
-        if t_probe * (cand * h * w / l_probe) ** 2 <= per_step_budget:
-            frames = cand
+
+    def pick(t_ref, l_ref):
+        for cand in range(f, 0, -1):   # self-attention time grows ~quadratically with the token count
+            if t_ref * (cand * h * w / l_ref) ** 2 <= per_step_budget:
+                return cand
+        return 1
+
+    # one frame is a poor predictor (small problems run the host cores inefficiently): re-estimate from the size just
+    # chosen until the estimate stops growing (at most two extra untimed runs)
+    frames = pick(t_probe, l_probe)
+    for _ in range(2):
+        t_big, l_big = run(frames)
+        better = pick(t_big, l_big)
+        if better <= frames:
             break
+        frames = better
     for _ in range(warmup):
         run(frames)
     times = [run(frames)[0] for _ in range(steps)]
