@@ -224,6 +224,45 @@ def test_short_key_kernel_single_cta_and_cta_pair_variants(ext, b, lq, lk, n, le
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 4e-3
 
 
+def test_fmha_randomized_shapes_all_variants_agree(ext):
+    """24 seeded random problems (B 1-3, heads 1-5, 1 <= Lq <= 1500, 1 <= Lk <= 5000, random k_lens incl. 0 and Lk):
+    the default kernels (CTA pairs for both key-length regimes) against the single-CTA variants and, on sampled query
+    rows, against an fp32 evaluation; split and unsplit schedules."""
+    import random
+    rng = random.Random(1234)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    for case in range(24):
+        b, n = rng.randint(1, 3), rng.randint(1, 5)
+        lq = rng.choice([1, 127, 128, 129, 255, 256, 257, 511, 512, 513, rng.randint(1, 1500)])
+        lk = rng.choice([1, 64, 127, 128, 129, 2047, 2048, 2049, 2176, rng.randint(1, 5000)])
+        q, k, v = (torch.randn(b, l, n, 128, device="cuda", generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+        lens = [rng.choice([0, 1, lk, rng.randint(0, lk)]) for _ in range(b)] if rng.random() < 0.6 else None
+        kl = None if lens is None else torch.tensor(lens, dtype=torch.int32, device="cuda")
+        got = ext.fmha_fwd(q, k, v, k_lens=kl)
+        got_ns = ext.fmha_fwd(q, k, v, k_lens=kl, split_units=False)
+        old = (ext.set_knob("fmha_pair", 0), ext.set_knob("xattn_pair", 0))
+        try:
+            single = ext.fmha_fwd(q, k, v, k_lens=kl)
+        finally:
+            ext.set_knob("fmha_pair", old[0])
+            ext.set_knob("xattn_pair", old[1])
+        tag = (case, b, n, lq, lk, lens)
+        assert torch.isfinite(got.float()).all(), tag
+        assert (got.float() - single.float()).abs().max().item() <= 4e-3, tag
+        assert (got.float() - got_ns.float()).abs().max().item() <= 4e-3, tag
+        # fp32 evaluation of up to 48 sampled rows per sample
+        rows = torch.tensor(sorted(set([0, lq - 1] + [rng.randrange(lq) for _ in range(46)])), device="cuda")
+        for bi in range(b):
+            k_len = lk if lens is None else lens[bi]
+            qf = q[bi, rows].float().transpose(0, 1)                         # [N, R, D]
+            sc = torch.matmul(qf, k[bi].float().permute(1, 2, 0)) * 128 ** -0.5
+            sc[:, :, k_len:] = float("-inf")
+            pr = torch.nan_to_num(torch.softmax(sc, dim=-1), nan=0.0)
+            want = torch.matmul(pr, v[bi].float().transpose(0, 1)).transpose(0, 1)     # [R, N, D]
+            err = (got[bi, rows].float() - want).abs().max().item()
+            assert err <= 2e-2, (tag, bi, err)
+
+
 def test_fmha_peaked_logits_exercise_the_lazy_rescale(ext):
     """Row maxima that grow by far more than 2^8 from one key tile to the next force the in-place
     rescale of the TMEM accumulator."""
