@@ -21,9 +21,12 @@ from oracle import wan_attention_oracle as orc
 pytestmark = pytest.mark.gpu
 
 CASES = {
-    # name: (dim, heads, L, grid (f, h, w), real tokens)
-    "toy": (1024, 8, 480, (3, 8, 19), 456),
-    "tiles": (1024, 8, 2560, (4, 20, 31), 2480),
+    # name: (dim, heads, L, grid (f, h, w) per sample, real tokens per sample)
+    "toy": (1024, 8, 480, [(3, 8, 19)], [456]),
+    "tiles": (1024, 8, 2560, [(4, 20, 31)], [2480]),
+    # batched CFG under sequence parallelism (B = 2, different padding per sample): the v projection then takes the
+    # head-scatter kernel instead of the GEMM's column-group epilogue (which handles B == 1)
+    "batch2": (1024, 8, 320, [(2, 8, 19), (2, 8, 17)], [304, 272]),
 }
 
 
@@ -37,8 +40,8 @@ def _inputs(case, layer):
     dim, heads, L, grid, real = CASES[case]
     g = torch.Generator().manual_seed(17)
     prm = orc.init_attention_params(dim, g, realistic_bias=True)
-    x = torch.randn(1, L, dim, generator=g).to(torch.bfloat16).float() + 0.25 * layer
-    return prm, x, torch.tensor([list(grid)]), torch.tensor([real])
+    x = torch.randn(len(real), L, dim, generator=g).to(torch.bfloat16).float() + 0.25 * layer
+    return prm, x, torch.tensor([list(gr) for gr in grid]), torch.tensor(real)
 
 
 def _worker(rank, world, port, out, transport, case):
@@ -76,7 +79,7 @@ def _worker(rank, world, port, out, transport, case):
                                             vf[:, rank * s:(rank + 1) * s], torch.tensor([L]))
             ref = att.flash_attention(qf, kf, vf)[:, rank * s:(rank + 1) * s]
         gerr = (gen.float() - ref.float()).abs().max().item()
-        used_p2p = p2p.context(1, s, heads, torch.device("cuda", rank)) is not None
+        used_p2p = p2p.context(len(CASES[case][4]), s, heads, torch.device("cuda", rank)) is not None
         out[rank] = (outs, self_err, gerr, str(gen.dtype), used_p2p)
         p2p.close_all()
     finally:
@@ -84,7 +87,7 @@ def _worker(rank, world, port, out, transport, case):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("case", ["toy", "tiles"])
+@pytest.mark.parametrize("case", ["toy", "tiles", "batch2"])
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sp_attention_matches_the_oracle(world, transport, case):
