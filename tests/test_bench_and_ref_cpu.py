@@ -81,3 +81,36 @@ def test_staged_reference_is_what_the_loader_uses_when_the_tree_is_absent(monkey
         assert os.path.isfile(os.path.join(staged, "models/wan/utils/modules/model.py"))
         if not os.path.isdir("/root/reference"):
             assert picked == staged
+
+
+@pytest.mark.parametrize("path", ["profiles/r02i/bench_r02i.json", "profiles/r02f/bench_8gpu_r02f.json"])
+def test_recorded_bench_lines_satisfy_the_contract(path):
+    """The committed bench lines (one GPU with the driver's --steps 20 --warmup 5, and 8 GPUs) carry every key the
+    bench contract names, with consistent arithmetic."""
+    line = json.loads([l for l in open(os.path.join(ROOT, path)).read().strip().splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in line, k
+    assert line["unit"] == "TFLOP/s" and line["dtype"] == "bf16" and line["data"] == "synthetic"
+    assert line["scaling"] == "strong" and line["vs_baseline"] is None and line["higher_is_better"] is True
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["config"]["video_tokens"] == 75600 and line["config"]["heads"] == 40       # same config at every N
+    # value = attention flop of the step / time
+    assert abs(line["attention_flop_per_step"] / (line["ms_per_step"] * 1e-3) * 1e-12 / line["value"] - 1) < 1e-6
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < line["value"]
+    rf = line["roofline"]
+    assert rf["bound"] == "tensor" and abs(rf["achieved"] / rf["peak"] - rf["frac"]) < 1e-9 and rf["frac"] < 1.0
+    assert line["gpu_launches"] > 0 and set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if line["n_gpus"] == 1:
+        cb = line["cpu_baseline"]
+        assert cb["kind"] == "reference" and cb["cores"] >= 1 and "sample" in cb
+        assert rf["traffic"] and 0.9 < rf["traffic"] / (4 * 75600 * 5120 * 2) < 1.2     # DRAM bytes vs algorithmic bytes
+        assert line["roofline_prologue"]["bound"] == "hbm" and "back_to_back" in line["roofline_prologue"]
+    else:
+        pc = line["parity_check"]
+        assert pc["ok"] is True and pc["max_abs_vs_fp32_rows"] <= 2e-2 and pc["cos_vs_fp32_rows"] >= 0.9999
+        assert "self_attention" in line["kernel_split"]["segments"]
+    den = line["denoise_step"]
+    assert den["ms"] > 0 and den["flop"] > line["attention_flop_per_step"] and 0 < den["frac_of_sustained_peak"] < 1.05
