@@ -202,6 +202,23 @@ def cpu_reference_rate(cfg, seconds_budget, steps, warmup):
     return (fs + fc) / sec * 1e-12, sec * 1e3, sample, threads, kind
 
 
+def workload_config(cfg, world, fused_exchange=True):
+    """The `config` object of the JSON line -- ONE definition for both arms, so the driver's same-config check compares
+    like with like: the reference arm names the workload it samples, the bounded sample itself is `cpu_baseline.sample`."""
+    f, h, w = cfg["grid"]
+    L = f * h * w
+    sharding = "none" if world == 1 else (
+        f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
+        if fused_exchange else f"Ulysses heads/{world} over NCCL all-to-all")
+    return {
+        "workload": cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, 512-key "
+                    "cross-attention) of all layers",
+        "sharding": sharding, "video_tokens": L, "text_tokens": cfg["text_len"], "dim": cfg["dim"],
+        "heads": cfg["heads"], "layers": cfg["layers"],
+        "l2_policy": f"inputs larger than L2: 4 rotating layer-input sets of {3 * (L // world) * cfg['dim'] * 2 / 1e6:.0f} "
+                     "MB each (GPU arm; the CPU reference arm runs the bounded sample named in cpu_baseline.sample)"}
+
+
 def run_reference_arm(args, cfg_key):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -213,7 +230,7 @@ def run_reference_arm(args, cfg_key):
         "impl": "reference", "metric": "dit_attention_tflops", "value": tflops, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": cfg["name"] + " -- attention stack", "sample": sample},
+        "config": workload_config(cfg, max(1, args.gpus)), "sample": sample,
         "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -625,11 +642,9 @@ def measure(env, args, cfg_key, steps, warmup, *, denoise=True, gemm_roofline=Tr
                     "flop = attention + block linears"}
         del model
         torch.cuda.empty_cache()
-    res["sharding"] = ("none" if world == 1 else (
-        f"Ulysses heads/{world}, exchange fused into the kernels over NVLink peer memory"
-        if ctx is not None else f"Ulysses heads/{world} over NCCL all-to-all"))
-    res["geometry"] = {"video_tokens": L, "text_tokens": text_len, "dim": dim, "heads": heads, "layers": layers,
-                       "l2_policy": f"inputs larger than L2: 4 rotating layer-input sets of {3 * s * dim * 2 / 1e6:.0f} MB each"}
+    res["config"] = workload_config(cfg, world, fused_exchange=ctx is not None)
+    res["sharding"] = res["config"]["sharding"]
+    res["geometry"] = {k: res["config"][k] for k in ("video_tokens", "text_tokens", "dim", "heads", "layers", "l2_policy")}
     return res
 
 
@@ -663,8 +678,7 @@ def run_native_arm(args, cfg_key):
             "metric": "dit_attention_tflops", "value": main["value"], "unit": "TFLOP/s", "n_gpus": env.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload=cfg["name"] + " -- attention stack (q/k RMSNorm + 3-D RoPE, self-attention, "
-                           "512-key cross-attention) of all layers", sharding=main["sharding"], **main["geometry"]),
+            "config": main["config"],
             "attention_flop_per_step": main["attention_flop_per_step"],
             "denoise_step_ms": (main.get("denoise_step") or {}).get("ms"),
             "denoise_step": main.get("denoise_step"),

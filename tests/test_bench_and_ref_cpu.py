@@ -46,6 +46,19 @@ def test_reference_arm_cli_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
     assert cb["value"] == line["value"] and cb["kind"] in ("reference", "port") and cb["cores"] == len(os.sched_getaffinity(0))
+    # the arm reports on the GPU arm's config object (one definition for both); the bounded sample is named beside it
+    assert line["config"] == bench.workload_config(bench.CONFIGS["1.3B"], 1) and line["sample"] == cb["sample"]
+
+
+def test_both_arms_share_one_config_object():
+    """workload_config is what both arms print: same keys as the recorded GPU lines, per-rank working set in l2_policy."""
+    rec = json.loads([l for l in open(os.path.join(ROOT, "profiles/r02i/bench_8gpu_r02i.json")).read().strip().splitlines()
+                      if l.startswith("{")][-1])["config"]
+    now = bench.workload_config(bench.CONFIGS[bench.HEADLINE], 8)
+    assert set(now) == set(rec)
+    assert {k: v for k, v in now.items() if k != "l2_policy"} == {k: v for k, v in rec.items() if k != "l2_policy"}
+    assert now["l2_policy"].startswith(rec["l2_policy"])
+    assert bench.workload_config(bench.CONFIGS[bench.HEADLINE], 1)["sharding"] == "none"
 
 
 @pytest.mark.skipif(not os.path.isfile("/root/reference/models/wan/utils/modules/model.py"), reason="/root/reference not mounted")
