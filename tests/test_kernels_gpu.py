@@ -224,6 +224,34 @@ def test_short_key_kernel_single_cta_and_cta_pair_variants(ext, b, lq, lk, n, le
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 4e-3
 
 
+@pytest.mark.parametrize("b,lq,lk,n,lens", [(4, 6000, 512, 6, [512, 100, 0, 300]), (3, 9000, 257, 5, [257, 257, 129]),
+                                             (2, 20000, 1000, 3, [128, 1000])])
+def test_short_key_kernel_many_units_per_cta_pair(ext, b, lq, lk, n, lens):
+    """More 512-row units than CTA pairs, so every pair walks several units back to back and the first score tiles of
+    a unit are issued inside the last step of its predecessor (fmha_fwd_sm100.cuh, MMA warp).  The key lengths make
+    consecutive units of one pair differ in their number of key tiles (4 -> 1 -> 0 -> 3, ...): primed and un-primed
+    unit starts, units without keys, one-step units (never primed from) all occur.  Against the oracle and against
+    the single-CTA variant, which starts every unit with its own prologue."""
+    g = torch.Generator().manual_seed(lq + 31 * lk)
+    q, k, v = (torch.randn(b, l, n, 128, generator=g).to(torch.bfloat16) for l in (lq, lk, lk))
+    kl = torch.tensor(lens, dtype=torch.int32)
+    bias = 0.1 * torch.randn(n * 128, generator=g)
+    w = torch.ones(lk)
+    w[:lk // 4] = 1.25
+    got = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=kl.cuda())
+    got_mod = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=kl.cuda(), key_pv_weight=w.cuda(), out_bias=bias.cuda())
+    old = ext.set_knob("xattn_pair", 0)
+    try:
+        single = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=kl.cuda())
+    finally:
+        ext.set_knob("xattn_pair", old)
+    _check_attn(got, orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32))
+    _check_attn(got_mod, orc.attention_varlen(q, k, v, k_lens=kl, compute_dtype=torch.float32, key_pv_weight=w, out_bias=bias))
+    assert (got.float() - single.float()).abs().max().item() <= 4e-3
+    again = ext.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), k_lens=kl.cuda())
+    assert torch.equal(got, again)                                   # no dependence on timing
+
+
 def test_fmha_randomized_shapes_all_variants_agree(ext):
     """24 seeded random problems (B 1-3, heads 1-5, 1 <= Lq <= 1500, 1 <= Lk <= 5000, random k_lens incl. 0 and Lk):
     the default kernels (CTA pairs for both key-length regimes) against the single-CTA variants and, on sampled query

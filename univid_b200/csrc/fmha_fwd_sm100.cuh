@@ -493,6 +493,13 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       int gstep = 0;    // softmax/MMA steps so far (all segments)
       [[maybe_unused]] long long pf_p0 = 0, pf_p1 = 0, pf_kv = 0, pf_q = 0;
       [[maybe_unused]] const long long pf_start = clock64();
+      // kQBufs == 2 (few key tiles per unit): the next unit's query block sits in the other buffer long before this
+      // unit ends, so its first score tiles are issued inside this unit's LAST step, at the point where a middle
+      // step issues the scores of its successor.  The unit boundary then looks like a step boundary to the tensor
+      // pipe: the softmax groups find S ready when they leave the epilogue instead of waiting for both tiles' last
+      // P, two PVs, and two Q K^T (wait-cycle profile of round 2: ~3500 cycles per 4-step unit).  Only behind a unit
+      // of >= 2 steps: the buffer the next Q loads into is released one softmax step into this unit.
+      bool scores_ahead = false;   // this unit's first score tiles were issued by the previous unit
       for (int si = 0; si < sch.n_seg; ++si) {
         const FmhaSeg sg = sch.seg(si);
         int batch, head, q_row0, k_len, ka, kb;
@@ -500,6 +507,19 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
         const int n_steps = kb - ka;
         const int qb = si % kQBufs;
         const uint32_t qpar = (si / kQBufs) & 1;
+        const bool primed = scores_ahead;
+        scores_ahead = false;
+        [[maybe_unused]] int nqb = 0;
+        [[maybe_unused]] uint32_t nqpar = 0;
+        if constexpr (kQBufs == 2 && SM::kPSmem && !kEarlyS) {
+          if (n_steps >= 2 && si + 1 < sch.n_seg) {
+            int nb, nh, nq0, nkl, nka, nkb;
+            decode(sch.seg(si + 1), nb, nh, nq0, nkl, nka, nkb);
+            scores_ahead = nkb > nka;
+            nqb = (si + 1) % kQBufs;
+            nqpar = ((si + 1) / kQBufs) & 1;
+          }
+        }
         UVB_PROF(pf_q, mbar_wait(&q_full[2 * qb], qpar));
         tc_fence_after();
         if (n_steps == 0) {
@@ -509,21 +529,24 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
           commit(&o_full[1]);
           continue;
         }
-        // prologue: scores of the first step of both tiles
-        UVB_PROF(pf_kv, wait_full(ring));
-        issue_qk(2 * qb, 0, ring);
-        commit(&s_full[0]);
-        mbar_wait(&q_full[2 * qb + 1], qpar);
-        tc_fence_after();
-        issue_qk(2 * qb + 1, 1, ring);
-        commit(&s_full[1]);
-        commit(&kv_empty[ring % kStages]);   // K tile of step 0 is fully consumed by the prologue
+        if (!primed) {
+          // prologue: scores of the first step of both tiles
+          UVB_PROF(pf_kv, wait_full(ring));
+          issue_qk(2 * qb, 0, ring);
+          commit(&s_full[0]);
+          mbar_wait(&q_full[2 * qb + 1], qpar);
+          tc_fence_after();
+          issue_qk(2 * qb + 1, 1, ring);
+          commit(&s_full[1]);
+          commit(&kv_empty[ring % kStages]);   // K tile of step 0 is fully consumed by the prologue
+        }
 
         for (int step = 0; step < n_steps; ++step) {
           const uint32_t par = (gstep + step) & 1;
           const int v_ring = ring + 2 * step + 1;
-          const int k_ring = v_ring + 1;          // K tile of the next step
+          const int k_ring = v_ring + 1;          // K tile of the next step (last step: first K tile of the next unit)
           const bool more = step + 1 < n_steps;
+          const bool ahead = more || scores_ahead;   // a successor score tile goes out during this step
           UVB_PROF(pf_kv, wait_full(v_ring));
           if constexpr (kEarlyS) {
             // S_t is free as soon as the softmax group holds it in registers (s_free), long before any of P_t exists:
@@ -560,9 +583,13 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
               // while the softmax still exponentiates the second half (which it hands over through shared
               // memory, not through S_t).  Only the last 64 keys of PV stay on the softmax -> MMA -> softmax
               // dependency chain; QK^T leaves it.
-              if (more) {
+              if (ahead) {
                 if (t == 0) UVB_PROF(pf_kv, wait_full(k_ring));
-                issue_qk(2 * qb + t, t, k_ring);
+                if (!more) {
+                  UVB_PROF(pf_q, mbar_wait(&q_full[2 * nqb + t], nqpar));
+                  tc_fence_after();
+                }
+                issue_qk(more ? 2 * qb + t : 2 * nqb + t, t, k_ring);
                 commit(&s_full[t]);
               }
               UVB_PROF(pf_p1, wait_p(&p_full[2 * t + 1], par));
@@ -583,7 +610,7 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
             }
           }
           commit(&kv_empty[v_ring % kStages]);
-          if (more) commit(&kv_empty[k_ring % kStages]);
+          if (ahead) commit(&kv_empty[k_ring % kStages]);
         }
         ring += 2 * n_steps;
         gstep += n_steps;
