@@ -185,7 +185,8 @@ struct FmhaSched {
 // of them is what lets the softmax keep ahead of the MMAs.
 // Lab builds only (-DUVB_FMHA_PROFILE): cycle counters of the barrier waits, per CTA 16 x u64 in FmhaParams::prof
 // [0..2] softmax group 0: total, waiting for S, waiting for PV; [3..5] group 1; [6..10] MMA warp: total, waiting for
-// P half 0, P half 1, K/V tiles, Q; [11] steps
+// P half 0, P half 1, K/V tiles, Q; [11] steps; [12..13] softmax group 0: unit set-up (top of a segment to its first
+// step), epilogue (end of the step loop to the end of the segment); [14..15] group 1
 #ifdef UVB_FMHA_PROFILE
 #define UVB_PROF(acc, stmt)          \
   do {                               \
@@ -663,7 +664,12 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       p.timeline[blockIdx.x * 32 + 1] = globaltimer_ns();
     }
 
+    [[maybe_unused]] long long pf_setup = 0, pf_epi = 0, pf_mark = 0;
     for (int si = 0; si < sch.n_seg; ++si) {
+#ifdef UVB_FMHA_PROFILE
+      const long long pf_top = clock64();
+      if (pf_mark != 0) pf_epi += pf_top - pf_mark;
+#endif
       if (p.timeline != nullptr && threadIdx.x == 0 && si > 0 && si < 30)
         p.timeline[blockIdx.x * 32 + 1 + si] = globaltimer_ns();
       const FmhaSeg sg = sch.seg(si);
@@ -672,6 +678,9 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       const int n_steps = kb - ka;
       float m = -INFINITY;  // running row max in raw-logit units
       float l = 0.f;        // running row sum of exp2((s - m) * scale_log2)
+#ifdef UVB_FMHA_PROFILE
+      pf_setup += clock64() - pf_top;
+#endif
 
       for (int step = 0; step < n_steps; ++step) {
         const uint32_t par = (gstep + step) & 1;
@@ -815,6 +824,9 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       }
       if constexpr (kQBufs == 2) release_pending();     // segments without steps
       gstep += n_steps;
+#ifdef UVB_FMHA_PROFILE
+      pf_mark = clock64();
+#endif
 
       // ------------------------------------- segment epilogue -------------------------------------
       mbar_wait(&o_full[t], si & 1);
@@ -1004,6 +1016,8 @@ fmha_fwd_kernel(const __grid_constant__ FmhaParams p) {
       pr[0] = clock64() - pf_start;
       pr[1] = pf_s;
       pr[2] = pf_pv;
+      p.prof[blockIdx.x * 16 + 12 + 2 * t] = pf_setup;
+      p.prof[blockIdx.x * 16 + 13 + 2 * t] = pf_epi + (pf_mark != 0 ? clock64() - pf_mark : 0);
     }
 #endif
     if (p.timeline != nullptr && threadIdx.x == 0)

@@ -280,6 +280,14 @@ static int run_fmha(int argc, char** argv) {
         printf("\n     per step: sm0 %.0f (S %.0f, PV %.0f)  sm1 %.0f (S %.0f, PV %.0f)  mma %.0f (P0 %.0f P1 %.0f KV %.0f)",
                sum[0] / n / steps, sum[1] / n / steps, sum[2] / n / steps, sum[3] / n / steps, sum[4] / n / steps,
                sum[5] / n / steps, sum[6] / n / steps, sum[7] / n / steps, sum[8] / n / steps, sum[9] / n / steps);
+      double extra[4] = {0};
+      for (int g = par; g < nsm; g += 2) {
+        if (!pr[g * 16 + 0]) continue;
+        for (int i = 0; i < 4; ++i) extra[i] += (double)pr[g * 16 + 12 + i];
+      }
+      if (steps > 0)
+        printf("\n     per step: sm0 set-up %.0f epilogue %.0f  sm1 set-up %.0f epilogue %.0f", extra[0] / n / steps,
+               extra[1] / n / steps, extra[2] / n / steps, extra[3] / n / steps);
       printf("\n");
     }
   }
